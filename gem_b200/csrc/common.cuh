@@ -1,0 +1,108 @@
+// gem_b200/csrc/common.cuh -- shared declarations of libgemb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/gemb200.h"
+
+namespace gemb {
+
+void set_error(const char *fmt, ...);
+
+#define GEMB_CUDA(call)                                                                       \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            gemb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,              \
+                            cudaGetErrorString(_e));                                          \
+            return GEMB_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define GEMB_TRY(call)                                                                        \
+    do {                                                                                      \
+        int _s = (call);                                                                      \
+        if (_s != GEMB_OK) return _s;                                                         \
+    } while (0)
+
+#define GEMB_ARG(cond, msg)                                                                   \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            gemb::set_error("bad argument: %s (%s)", msg, #cond);                             \
+            return GEMB_ERR_ARG;                                                              \
+        }                                                                                     \
+    } while (0)
+
+// ---- NCCL, resolved lazily with dlopen so that the single-GPU path has no NCCL dependency
+//      and so that a process that already loaded torch's libnccl.so.2 shares it.
+struct NcclApi;
+NcclApi *nccl_api();  // nullptr (and error set) if libnccl cannot be loaded
+
+struct Timer {  // pairs of events on ctx->stream, summed on demand
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    int begin(cudaStream_t s);
+    int end(cudaStream_t s);
+    double total_ms();  // synchronises on the recorded events
+    void reset() { used = 0; }
+    void destroy();
+};
+
+}  // namespace gemb
+
+struct gemb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // multi-GPU
+    int rank = 0, nranks = 1;
+    void *comm = nullptr;  // ncclComm_t
+    gemb::Timer t_spmm, t_dense, t_comm, t_misc;
+};
+
+struct gemb_csr_dev {
+    int64_t nnz = 0;
+    int32_t *indptr = nullptr;   // n_local + 1
+    int32_t *indices = nullptr;  // nnz, global column ids
+    float *data = nullptr;       // nnz or nullptr (unit weights)
+};
+
+struct gemb_graph {
+    gemb_ctx *ctx = nullptr;
+    int64_t n = 0;        // global number of nodes
+    int64_t row0 = 0;     // first row of this shard
+    int64_t n_local = 0;  // real rows of this shard
+    int64_t n_shard = 0;  // rows per rank used for collectives (= ceil(n / nranks)); n_local <= n_shard
+    int64_t n_pad = 0;    // n_shard * nranks
+    bool symmetric = false;
+    gemb_csr_dev A, AT;   // AT aliases A when symmetric
+};
+
+namespace gemb {
+
+// ---- spmm.cu
+// Y[n_rows x b] = X0 + alpha * A * X ; X has leading dimension ldx (>= b), rows indexed by the
+// global column ids in A.  X0/Y are row shards (ld = b).  All device pointers.
+int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha,
+                const float *X, const float *X0, float *Y);
+
+// ---- dense.cu
+// G[b1 x b2] (fp64, row-major, OVERWRITTEN) = P^T Q over n rows (P: n x b1, Q: n x b2, fp32).
+int gram_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G);
+// Out[n x b2] = Q[n x b1] * M[b1 x b2]  (M fp32 device, row-major, ld = ldm). Out may not alias Q.
+int apply_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *M, int ldm, int b2,
+                 float *Out, int ldo);
+// Small b x b factorizations, single CTA, fp64 (device pointers):
+//  chol_inverse: G (b x b, SPD up to rank deficiency) -> Minv fp32 (b x b) with G = R^T R, Minv = R^-1
+//  (columns whose pivot falls below eps*max are zeroed: Q*Minv then has zero columns there).
+int chol_inverse_launch(gemb_ctx *ctx, int b, double *G, float *Minv, int *rank_out_dev);
+//  eigh: G -> eigenvalues w ascending (b), eigenvectors Z (b x b, column j <-> w[j]); G destroyed.
+int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Zscratch /* b x b */);
+int randn_launch(gemb_ctx *ctx, int64_t n, int b, uint64_t seed, uint64_t row_offset, float *X);
+// sum of squares of all entries (fp64 accumulate) -> out_dev[0]
+int sumsq_launch(gemb_ctx *ctx, int64_t count, const float *X, double *out_dev);
+int scale_launch(gemb_ctx *ctx, int64_t count, float s, float *X);
+
+}  // namespace gemb

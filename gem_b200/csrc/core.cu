@@ -1,0 +1,263 @@
+// gem_b200/csrc/core.cu -- context, errors, pinned memory, NCCL bootstrap, graph upload.
+#include "common.cuh"
+#include "nccl_api.h"
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+namespace gemb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int Timer::begin(cudaStream_t s) {
+    if (used + 2 > ev.size()) {
+        size_t old = ev.size();
+        ev.resize(old + 64);
+        for (size_t i = old; i < ev.size(); i++) GEMB_CUDA(cudaEventCreate(&ev[i]));
+    }
+    GEMB_CUDA(cudaEventRecord(ev[used], s));
+    return GEMB_OK;
+}
+int Timer::end(cudaStream_t s) {
+    GEMB_CUDA(cudaEventRecord(ev[used + 1], s));
+    used += 2;
+    return GEMB_OK;
+}
+double Timer::total_ms() {
+    double t = 0;
+    for (size_t i = 0; i + 1 < used; i += 2) {
+        float ms = 0;
+        if (cudaEventSynchronize(ev[i + 1]) != cudaSuccess) return -1;
+        if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess) return -1;
+        t += ms;
+    }
+    return t;
+}
+void Timer::destroy() {
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+    used = 0;
+}
+
+static NcclApi g_nccl;
+static int g_nccl_state = 0;  // 0 untried, 1 ok, -1 failed
+
+NcclApi *nccl_api() {
+    if (g_nccl_state == 1) return &g_nccl;
+    if (g_nccl_state == -1) return nullptr;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        set_error("cannot dlopen libnccl.so.2: %s", dlerror());
+        g_nccl_state = -1;
+        return nullptr;
+    }
+#define LOAD(name)                                                      \
+    g_nccl.name = (decltype(g_nccl.name))dlsym(h, "nccl" #name);        \
+    if (!g_nccl.name) {                                                 \
+        set_error("libnccl lacks symbol nccl" #name);                   \
+        g_nccl_state = -1;                                              \
+        return nullptr;                                                 \
+    }
+    LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(AllGather)
+    LOAD(GetErrorString) LOAD(GetVersion)
+#undef LOAD
+    g_nccl_state = 1;
+    return &g_nccl;
+}
+
+}  // namespace gemb
+
+using namespace gemb;
+
+extern "C" {
+
+int gemb_version(void) { return GEMB_VERSION; }
+const char *gemb_last_error(void) { return g_err; }
+
+int gemb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gemb_ctx_create(int device, gemb_ctx **out) {
+    GEMB_ARG(out != nullptr, "out");
+    int n = gemb_device_count();
+    if (n <= 0) {
+        set_error("no CUDA device visible: libgemb200 has no CPU fallback");
+        return GEMB_ERR_CUDA;
+    }
+    GEMB_ARG(device >= 0 && device < n, "device index");
+    GEMB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GEMB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libgemb200 is built for sm_100a only", device, prop.major,
+                  prop.minor);
+        return GEMB_ERR_CUDA;
+    }
+    gemb_ctx *c = new gemb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    GEMB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return GEMB_OK;
+}
+
+int gemb_ctx_destroy(gemb_ctx *c) {
+    if (!c) return GEMB_OK;
+    cudaSetDevice(c->device);
+    if (c->comm) {
+        NcclApi *api = nccl_api();
+        if (api) api->CommDestroy((ncclComm_t)c->comm);
+    }
+    c->t_spmm.destroy();
+    c->t_dense.destroy();
+    c->t_comm.destroy();
+    c->t_misc.destroy();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return GEMB_OK;
+}
+
+int gemb_host_alloc(size_t bytes, void **out) {
+    GEMB_ARG(out != nullptr, "out");
+    GEMB_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return GEMB_OK;
+}
+int gemb_host_free(void *p) {
+    if (p) GEMB_CUDA(cudaFreeHost(p));
+    return GEMB_OK;
+}
+
+int gemb_comm_unique_id(void *id_out) {
+    GEMB_ARG(id_out != nullptr, "id_out");
+    NcclApi *api = nccl_api();
+    if (!api) return GEMB_ERR_NCCL;
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) {
+        set_error("ncclGetUniqueId: %s", api->GetErrorString(r));
+        return GEMB_ERR_NCCL;
+    }
+    static_assert(sizeof(id) == GEMB_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    memcpy(id_out, &id, sizeof id);
+    return GEMB_OK;
+}
+
+int gemb_comm_init(gemb_ctx *c, int rank, int nranks, const void *idp) {
+    GEMB_ARG(c && idp, "ctx/id");
+    GEMB_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "rank/nranks");
+    NcclApi *api = nccl_api();
+    if (!api) return GEMB_ERR_NCCL;
+    GEMB_CUDA(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, idp, sizeof id);
+    ncclComm_t comm;
+    ncclResult_t r = api->CommInitRank(&comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        set_error("ncclCommInitRank: %s", api->GetErrorString(r));
+        return GEMB_ERR_NCCL;
+    }
+    c->comm = comm;
+    c->rank = rank;
+    c->nranks = nranks;
+    return GEMB_OK;
+}
+
+static int upload_csr(gemb_ctx *c, int64_t n_local, const int32_t *indptr, const int32_t *indices,
+                      const float *data, gemb_csr_dev *d) {
+    int64_t nnz = indptr[n_local] - indptr[0];
+    GEMB_ARG(indptr[0] == 0, "indptr[0] must be 0 (shard-local offsets)");
+    GEMB_ARG(nnz >= 0 && nnz < (int64_t)2147483647, "nnz per shard must be < 2^31");
+    d->nnz = nnz;
+    GEMB_CUDA(cudaMalloc(&d->indptr, sizeof(int32_t) * (n_local + 1)));
+    GEMB_CUDA(cudaMalloc(&d->indices, sizeof(int32_t) * (nnz > 0 ? nnz : 1)));
+    GEMB_CUDA(cudaMemcpyAsync(d->indptr, indptr, sizeof(int32_t) * (n_local + 1),
+                              cudaMemcpyHostToDevice, c->stream));
+    if (nnz)
+        GEMB_CUDA(cudaMemcpyAsync(d->indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice,
+                                  c->stream));
+    if (data && nnz) {
+        GEMB_CUDA(cudaMalloc(&d->data, sizeof(float) * nnz));
+        GEMB_CUDA(cudaMemcpyAsync(d->data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice,
+                                  c->stream));
+    }
+    return GEMB_OK;
+}
+
+int gemb_graph_upload(gemb_ctx *c, int64_t n, int64_t row0, int64_t n_local, const int32_t *indptr,
+                      const int32_t *indices, const float *data, const int32_t *indptr_t,
+                      const int32_t *indices_t, const float *data_t, gemb_graph **out) {
+    GEMB_ARG(c && out && indptr, "ctx/out/indptr");
+    GEMB_ARG(n > 0 && n < (int64_t)2147483647, "n");
+    GEMB_ARG(row0 >= 0 && n_local >= 0 && row0 + n_local <= n, "row range");
+    GEMB_ARG(indices != nullptr || indptr[n_local] == 0, "indices");
+    GEMB_CUDA(cudaSetDevice(c->device));
+    gemb_graph *g = new gemb_graph();
+    g->ctx = c;
+    g->n = n;
+    g->row0 = row0;
+    g->n_local = n_local;
+    g->n_shard = (n + c->nranks - 1) / c->nranks;
+    g->n_pad = g->n_shard * c->nranks;
+    if (c->nranks > 1) {
+        if (row0 != g->n_shard * c->rank || n_local > g->n_shard) {
+            set_error("multi-GPU shard must be rows [rank*ceil(n/P), ...): got row0=%lld n_local=%lld",
+                      (long long)row0, (long long)n_local);
+            delete g;
+            return GEMB_ERR_ARG;
+        }
+    } else {
+        if (row0 != 0 || n_local != n) {
+            set_error("single-GPU upload needs row0=0, n_local=n");
+            delete g;
+            return GEMB_ERR_ARG;
+        }
+    }
+    int s = upload_csr(c, n_local, indptr, indices, data, &g->A);
+    if (s != GEMB_OK) { gemb_graph_free(g); return s; }
+    if (indptr_t) {
+        s = upload_csr(c, n_local, indptr_t, indices_t, data_t, &g->AT);
+        if (s != GEMB_OK) { gemb_graph_free(g); return s; }
+        g->symmetric = false;
+    } else {
+        g->AT = g->A;
+        g->symmetric = true;
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        set_error("graph upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        gemb_graph_free(g);
+        return GEMB_ERR_CUDA;
+    }
+    *out = g;
+    return GEMB_OK;
+}
+
+int gemb_graph_free(gemb_graph *g) {
+    if (!g) return GEMB_OK;
+    cudaSetDevice(g->ctx->device);
+    if (!g->symmetric) {
+        cudaFree(g->AT.indptr);
+        cudaFree(g->AT.indices);
+        cudaFree(g->AT.data);
+    }
+    cudaFree(g->A.indptr);
+    cudaFree(g->A.indices);
+    cudaFree(g->A.data);
+    delete g;
+    return GEMB_OK;
+}
+
+}  // extern "C"

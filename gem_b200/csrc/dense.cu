@@ -1,0 +1,439 @@
+// gem_b200/csrc/dense.cu -- tall-skinny dense kernels of the HOPE solver (round-1 CUDA-core version).
+//
+//   gram   : G = P^T Q      (n x b1, n x b2 -> b1 x b2), the CholeskyQR / Rayleigh-Ritz contraction
+//   apply  : Out = Q * M    (n x b1 times b1 x b2)
+//   chol_inverse, eigh : single-CTA fp64 factorizations of the b x b matrices
+// These replace numpy.linalg.qr / svd inside scipy's svds (hope.py:33 -> _svds.py:508-533).
+// fp32 data, fp32 FMA inside a CTA's partial sums, fp64 across CTAs and in the b x b algebra.
+#include "common.cuh"
+
+namespace gemb {
+
+// ------------------------------------------------------------------------------------ gram
+// Output tile (16*TM) x (16*TM) per blockIdx.y, rows strided over blockIdx.x in chunks of KC.
+template <int TM>
+__global__ void __launch_bounds__(256)
+gram_kernel(int64_t n, const float *__restrict__ P, int b1, const float *__restrict__ Q, int b2,
+            double *__restrict__ G, int tiles_n) {
+    constexpr int BT = 16 * TM;
+    constexpr int KC = 32;
+    __shared__ float sP[KC][BT];
+    __shared__ float sQ[KC][BT];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int tile_m = blockIdx.y / tiles_n, tile_n = blockIdx.y % tiles_n;
+    const int m0 = tile_m * BT, n0 = tile_n * BT;
+    float acc[TM][TM];
+#pragma unroll
+    for (int i = 0; i < TM; i++)
+#pragma unroll
+        for (int j = 0; j < TM; j++) acc[i][j] = 0.f;
+
+    for (int64_t r0 = (int64_t)blockIdx.x * KC; r0 < n; r0 += (int64_t)gridDim.x * KC) {
+        for (int idx = tid; idx < KC * BT; idx += 256) {
+            const int kk = idx / BT, col = idx - kk * BT;
+            const int64_t r = r0 + kk;
+            float vp = 0.f, vq = 0.f;
+            if (r < n) {
+                if (m0 + col < b1) vp = __ldg(P + r * b1 + m0 + col);
+                if (n0 + col < b2) vq = __ldg(Q + r * b2 + n0 + col);
+            }
+            sP[kk][col] = vp;
+            sQ[kk][col] = vq;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < KC; kk++) {
+            float a[TM], bb[TM];
+#pragma unroll
+            for (int i = 0; i < TM; i++) a[i] = sP[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TM; j++) bb[j] = sQ[kk][tx * TM + j];
+#pragma unroll
+            for (int i = 0; i < TM; i++)
+#pragma unroll
+                for (int j = 0; j < TM; j++) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; i++) {
+        const int gm = m0 + ty * TM + i;
+        if (gm >= b1) continue;
+#pragma unroll
+        for (int j = 0; j < TM; j++) {
+            const int gn = n0 + tx * TM + j;
+            if (gn < b2) atomicAdd(G + (size_t)gm * b2 + gn, (double)acc[i][j]);
+        }
+    }
+}
+
+static int pick_tm(int b) {
+    // tile edge 16*TM for TM in {4,5,6,8}: minimise padded area, prefer fewer tiles on ties
+    int best = 4;
+    long best_cost = -1;
+    const int cand[4] = {4, 5, 6, 8};
+    for (int t = 0; t < 4; t++) {
+        int bt = 16 * cand[t];
+        long tiles = (b + bt - 1) / bt;
+        long cost = tiles * bt;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cand[t]; }
+    }
+    return best;
+}
+
+int gram_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G) {
+    GEMB_CUDA(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)b1 * b2, ctx->stream));
+    if (n == 0) return GEMB_OK;
+    const int bmax = b1 > b2 ? b1 : b2;
+    const int TM = pick_tm(bmax);
+    const int BT = 16 * TM;
+    const int tiles_m = (b1 + BT - 1) / BT, tiles_n = (b2 + BT - 1) / BT;
+    int64_t chunks = (n + 31) / 32;
+    int gx = ctx->sm_count * 4 / (tiles_m * tiles_n);
+    if (gx < 1) gx = 1;
+    if (gx > chunks) gx = (int)chunks;
+    dim3 grid(gx, tiles_m * tiles_n), block(256);
+    switch (TM) {
+        case 4: gram_kernel<4><<<grid, block, 0, ctx->stream>>>(n, P, b1, Q, b2, G, tiles_n); break;
+        case 5: gram_kernel<5><<<grid, block, 0, ctx->stream>>>(n, P, b1, Q, b2, G, tiles_n); break;
+        case 6: gram_kernel<6><<<grid, block, 0, ctx->stream>>>(n, P, b1, Q, b2, G, tiles_n); break;
+        default: gram_kernel<8><<<grid, block, 0, ctx->stream>>>(n, P, b1, Q, b2, G, tiles_n); break;
+    }
+    GEMB_CUDA(cudaGetLastError());
+    return GEMB_OK;
+}
+
+// ------------------------------------------------------------------------------------ apply
+// Out[r, n0 + ..] = sum_k Q[r, k] * M[k, ..];  CTA tile: 64 rows x (16*TN) columns, K chunks of 16.
+template <int TN>
+__global__ void __launch_bounds__(256)
+apply_kernel(int64_t n, const float *__restrict__ Q, int b1, const float *__restrict__ M, int ldm,
+             int b2, float *__restrict__ Out, int ldo) {
+    constexpr int BN = 16 * TN;
+    constexpr int BM = 64, BK = 16;
+    __shared__ float sA[BK][BM + 1];
+    __shared__ float sB[BK][BN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;  // ty -> 4 rows, tx -> TN columns
+    const int64_t r0 = (int64_t)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    float acc[4][TN];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < b1; k0 += BK) {
+        for (int idx = tid; idx < BM * BK; idx += 256) {
+            const int rr = idx / BK, kk = idx - rr * BK;
+            const int64_t r = r0 + rr;
+            sA[kk][rr] = (r < n && k0 + kk < b1) ? __ldg(Q + r * b1 + k0 + kk) : 0.f;
+        }
+        for (int idx = tid; idx < BK * BN; idx += 256) {
+            const int kk = idx / BN, col = idx - kk * BN;
+            sB[kk][col] = (k0 + kk < b1 && n0 + col < b2) ? __ldg(M + (size_t)(k0 + kk) * ldm + n0 + col) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            float a[4], bb[TN];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < TN; j++) bb[j] = sB[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t r = r0 + ty * 4 + i;
+        if (r >= n) continue;
+#pragma unroll
+        for (int j = 0; j < TN; j++) {
+            const int col = n0 + tx * TN + j;
+            if (col < b2) Out[r * ldo + col] = acc[i][j];
+        }
+    }
+}
+
+int apply_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *M, int ldm, int b2,
+                 float *Out, int ldo) {
+    if (n == 0 || b2 == 0) return GEMB_OK;
+    const int TN = pick_tm(b2);
+    const int BN = 16 * TN;
+    dim3 grid((unsigned)((n + 63) / 64), (b2 + BN - 1) / BN), block(256);
+    switch (TN) {
+        case 4: apply_kernel<4><<<grid, block, 0, ctx->stream>>>(n, Q, b1, M, ldm, b2, Out, ldo); break;
+        case 5: apply_kernel<5><<<grid, block, 0, ctx->stream>>>(n, Q, b1, M, ldm, b2, Out, ldo); break;
+        case 6: apply_kernel<6><<<grid, block, 0, ctx->stream>>>(n, Q, b1, M, ldm, b2, Out, ldo); break;
+        default: apply_kernel<8><<<grid, block, 0, ctx->stream>>>(n, Q, b1, M, ldm, b2, Out, ldo); break;
+    }
+    GEMB_CUDA(cudaGetLastError());
+    return GEMB_OK;
+}
+
+// ------------------------------------------------------------------------------------ chol_inverse
+// G (b x b fp64, symmetric) -> Minv = R^-1 (fp32, upper triangular) with G = R^T R.
+// Work on the diagonally scaled matrix D^-1/2 G D^-1/2 (unit diagonal) so that the rank test is
+// scale free.  A pivot below PIV_EPS marks the column numerically dependent: its column of Minv is
+// zero (the orthonormalised block then carries a zero column, which stays zero under S).
+#define GEMB_PIV_EPS 1e-5
+__global__ void __launch_bounds__(1024)
+chol_inverse_kernel(int b, double *__restrict__ G, float *__restrict__ Minv, int *__restrict__ rank_out) {
+    extern __shared__ double sh[];
+    double *dscale = sh;           // b : 1/sqrt(G_jj) (0 if G_jj <= 0)
+    double *Linv = sh + b;         // b : 1.0 if column j kept, 0.0 if numerically dependent
+    __shared__ int s_rank;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // scale
+    for (int j = tid; j < b; j += nt) {
+        const double d = G[(size_t)j * b + j];
+        dscale[j] = d > 0.0 ? rsqrt(d) : 0.0;
+    }
+    if (tid == 0) s_rank = 0;
+    __syncthreads();
+    for (int idx = tid; idx < b * b; idx += nt) {
+        const int i = idx / b, j = idx - i * b;
+        G[idx] = G[idx] * dscale[i] * dscale[j];
+    }
+    __syncthreads();
+    // right-looking Cholesky on the lower triangle: L overwrites G (lower), flags in Linv[j] (0/1)
+    for (int j = 0; j < b; j++) {
+        if (tid == 0) {
+            const double d = G[(size_t)j * b + j];
+            if (d > GEMB_PIV_EPS) {
+                G[(size_t)j * b + j] = sqrt(d);
+                Linv[j] = 1.0;
+                s_rank++;
+            } else {
+                G[(size_t)j * b + j] = 0.0;
+                Linv[j] = 0.0;
+            }
+        }
+        __syncthreads();
+        const double ljj = G[(size_t)j * b + j];
+        const double inv = ljj > 0.0 ? 1.0 / ljj : 0.0;
+        for (int i = j + 1 + tid; i < b; i += nt) G[(size_t)i * b + j] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: G[i][k] -= L[i][j] * L[k][j], j < k <= i
+        const int m = b - j - 1;
+        for (int idx = tid; idx < m * m; idx += nt) {
+            const int ii = idx / m, kk = idx - ii * m;
+            if (kk <= ii) {
+                const int i = j + 1 + ii, k = j + 1 + kk;
+                G[(size_t)i * b + k] -= G[(size_t)i * b + j] * G[(size_t)k * b + j];
+            }
+        }
+        __syncthreads();
+    }
+    // R^-1 = D^-1/2 * L^-T.  Column c of L^-1 by forward substitution (thread per column), then
+    // Minv[r][c'] = dscale[r] * (L^-1)[c'][r]   for r <= c'.
+    // Store X = L^-1 into the (now free) strict upper triangle + separate diagonal array.
+    double *xdiag = sh + 2 * b;  // b
+    for (int c = tid; c < b; c += nt) {
+        // solve L x = e_c ; x_i for i >= c ; keep x in upper triangle: U[c][i] := x_i (i > c)
+        const bool okc = Linv[c] != 0.0;
+        const double xc = okc ? 1.0 / G[(size_t)c * b + c] : 0.0;
+        xdiag[c] = xc;
+        for (int i = c + 1; i < b; i++) {
+            double s = 0.0;
+            if (okc && Linv[i] != 0.0) {
+                s = G[(size_t)i * b + c] * xc;
+                for (int k = c + 1; k < i; k++) s += G[(size_t)i * b + k] * G[(size_t)c * b + k];
+                s = -s / G[(size_t)i * b + i];
+            }
+            G[(size_t)c * b + i] = s;  // (L^-1)[i][c]
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < b * b; idx += nt) {
+        const int r = idx / b, c = idx - r * b;  // Minv[r][c] = dscale[r] * (L^-1)[c][r], r <= c
+        double v = 0.0;
+        if (r == c) v = xdiag[r] * dscale[r];
+        else if (r < c) v = G[(size_t)r * b + c] * dscale[r];
+        Minv[idx] = (float)v;
+    }
+    if (tid == 0 && rank_out) *rank_out = s_rank;
+}
+
+int chol_inverse_launch(gemb_ctx *ctx, int b, double *G, float *Minv, int *rank_out_dev) {
+    const size_t sh = sizeof(double) * 3 * (size_t)b;
+    chol_inverse_kernel<<<1, 1024, sh, ctx->stream>>>(b, G, Minv, rank_out_dev);
+    GEMB_CUDA(cudaGetLastError());
+    return GEMB_OK;
+}
+
+// ------------------------------------------------------------------------------------ eigh
+// Two-sided cyclic Jacobi with round-robin (circle-method) pair ordering, one CTA, fp64.
+// A is destroyed; w ascending; Z column j <-> w[j].  Zt is b x b scratch.
+__global__ void __launch_bounds__(1024)
+eigh_jacobi_kernel(int b, double *__restrict__ A, double *__restrict__ w, double *__restrict__ Z,
+                   double *__restrict__ Zt, int max_sweeps, double rel_tol) {
+    extern __shared__ double sh[];
+    const int m = (b + 1) & ~1;     // even number of players; index >= b is a dummy
+    const int half = m / 2;
+    double *cs = sh;                // half
+    double *sn = sh + half;         // half
+    int *pp = (int *)(sh + 2 * half);
+    int *qq = pp + half;
+    __shared__ double s_off, s_diag;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int idx = tid; idx < b * b; idx += nt) Zt[idx] = (idx / b == idx % b) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int sweep = 0; sweep < max_sweeps; sweep++) {
+        if (tid == 0) { s_off = 0.0; s_diag = 0.0; }
+        __syncthreads();
+        double off = 0.0, dg = 0.0;
+        for (int idx = tid; idx < b * b; idx += nt) {
+            const int i = idx / b, j = idx - i * b;
+            const double v = A[idx];
+            if (i == j) dg += v * v; else off += v * v;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            off += __shfl_xor_sync(0xffffffffu, off, o);
+            dg += __shfl_xor_sync(0xffffffffu, dg, o);
+        }
+        if ((tid & 31) == 0) { atomicAdd(&s_off, off); atomicAdd(&s_diag, dg); }
+        __syncthreads();
+        if (s_off <= rel_tol * rel_tol * (s_diag + s_off) || s_diag + s_off == 0.0) break;
+        for (int r = 0; r < m - 1; r++) {
+            if (tid < half) {
+                int p, q;
+                if (tid == 0) { p = m - 1; q = r % (m - 1); }
+                else { p = (r + tid) % (m - 1); q = (r + m - 1 - tid) % (m - 1); }
+                if (p > q) { int t = p; p = q; q = t; }
+                double c = 1.0, s = 0.0;
+                if (q < b) {
+                    const double apq = A[(size_t)p * b + q];
+                    if (apq != 0.0) {
+                        const double app = A[(size_t)p * b + p], aqq = A[(size_t)q * b + q];
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = rsqrt(t * t + 1.0);
+                        s = t * c;
+                    }
+                } else { q = -1; }
+                pp[tid] = p; qq[tid] = q; cs[tid] = c; sn[tid] = s;
+            }
+            __syncthreads();
+            // columns: A <- A J, Zt <- Zt J
+            for (int idx = tid; idx < half * b; idx += nt) {
+                const int pi = idx / b, k = idx - pi * b;
+                const int p = pp[pi], q = qq[pi];
+                if (q < 0) continue;
+                const double c = cs[pi], s = sn[pi];
+                if (s == 0.0) continue;
+                double x = A[(size_t)k * b + p], y = A[(size_t)k * b + q];
+                A[(size_t)k * b + p] = c * x - s * y;
+                A[(size_t)k * b + q] = s * x + c * y;
+                x = Zt[(size_t)k * b + p]; y = Zt[(size_t)k * b + q];
+                Zt[(size_t)k * b + p] = c * x - s * y;
+                Zt[(size_t)k * b + q] = s * x + c * y;
+            }
+            __syncthreads();
+            // rows: A <- J^T A
+            for (int idx = tid; idx < half * b; idx += nt) {
+                const int pi = idx / b, k = idx - pi * b;
+                const int p = pp[pi], q = qq[pi];
+                if (q < 0) continue;
+                const double c = cs[pi], s = sn[pi];
+                if (s == 0.0) continue;
+                const double x = A[(size_t)p * b + k], y = A[(size_t)q * b + k];
+                A[(size_t)p * b + k] = c * x - s * y;
+                A[(size_t)q * b + k] = s * x + c * y;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // sort ascending by rank counting, permute eigenvector columns
+    for (int j = tid; j < b; j += nt) {
+        const double wj = A[(size_t)j * b + j];
+        int rank = 0;
+        for (int i = 0; i < b; i++) {
+            const double wi = A[(size_t)i * b + i];
+            rank += (wi < wj) || (wi == wj && i < j);
+        }
+        w[rank] = wj;
+        for (int k = 0; k < b; k++) Z[(size_t)k * b + rank] = Zt[(size_t)k * b + j];
+    }
+}
+
+int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Zscratch) {
+    const int half = ((b + 1) & ~1) / 2;
+    const size_t sh = sizeof(double) * 2 * half + sizeof(int) * 2 * half + 16;
+    eigh_jacobi_kernel<<<1, 1024, sh, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-13);
+    GEMB_CUDA(cudaGetLastError());
+    return GEMB_OK;
+}
+
+// ------------------------------------------------------------------------------------ misc
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+// standard normal per (global row, column): independent of the sharding
+__global__ void randn_kernel(int64_t n, int b, uint64_t seed, uint64_t row_offset, float *__restrict__ X) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * b) return;
+    const int64_t r = idx / b;
+    const int c = (int)(idx - r * b);
+    const uint64_t h = splitmix64(seed ^ splitmix64(((uint64_t)(r + row_offset) << 12) ^ (uint64_t)c));
+    const uint32_t u1 = (uint32_t)(h >> 32), u2 = (uint32_t)h;
+    const float f1 = ((float)u1 + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+    const float f2 = (float)u2 * 2.3283064365386963e-10f;
+    X[idx] = sqrtf(-2.0f * logf(f1)) * cospif(2.0f * f2);
+}
+
+int randn_launch(gemb_ctx *ctx, int64_t n, int b, uint64_t seed, uint64_t row_offset, float *X) {
+    const int64_t tot = n * b;
+    if (tot == 0) return GEMB_OK;
+    randn_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(n, b, seed, row_offset, X);
+    GEMB_CUDA(cudaGetLastError());
+    return GEMB_OK;
+}
+
+__global__ void sumsq_kernel(int64_t count, const float *__restrict__ X, double *__restrict__ out) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = X[i];
+        acc += v * v;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+int sumsq_launch(gemb_ctx *ctx, int64_t count, const float *X, double *out_dev) {
+    GEMB_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), ctx->stream));
+    if (count == 0) return GEMB_OK;
+    int grid = ctx->sm_count * 8;
+    if ((int64_t)grid * 256 > count) grid = (int)((count + 255) / 256);
+    sumsq_kernel<<<grid, 256, 0, ctx->stream>>>(count, X, out_dev);
+    GEMB_CUDA(cudaGetLastError());
+    return GEMB_OK;
+}
+
+__global__ void scale_kernel(int64_t count, float s, float *__restrict__ X) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x)
+        X[i] *= s;
+}
+
+int scale_launch(gemb_ctx *ctx, int64_t count, float s, float *X) {
+    if (count == 0) return GEMB_OK;
+    int grid = ctx->sm_count * 8;
+    if ((int64_t)grid * 256 > count) grid = (int)((count + 255) / 256);
+    scale_kernel<<<grid, 256, 0, ctx->stream>>>(count, s, X);
+    GEMB_CUDA(cudaGetLastError());
+    return GEMB_OK;
+}
+
+}  // namespace gemb

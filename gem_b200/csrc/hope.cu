@@ -1,0 +1,391 @@
+// gem_b200/csrc/hope.cu -- HOPE: top-k SVD of the Katz proximity S = (I - beta A)^-1 beta A without
+// ever forming S (replaces hope.py:29-36 and scipy svds, _svds.py:432-535).
+//
+// Algorithm (block subspace iteration with Rayleigh-Ritz on S^T S, the block form of what ARPACK
+// does for svds: SURVEY Appendix B):
+//     V <- orth(randn(n, b))                                   b = k + oversample
+//     repeat
+//         U  = S V                       J Horner sweeps of CSR SpMM      (katz)
+//         T  = U^T U  = V^T S^T S V ;  (theta, Z) = eigh(T)    Ritz values theta = sigma^2
+//         stop if the top-k theta moved by <= tol * theta_max  (or max_iters)
+//         U <- U R^-1   (CholeskyQR from T)
+//         W  = S^T U ;  V <- orth(W)     (CholeskyQR2)
+//     sigma_j = sqrt(theta_j) ascending over the top k;  X = [ U Z_k theta^-1/4 | V Z_k theta^1/4 ]
+//       (U = S V un-normalised:  U Z_k / sigma = left vectors, V Z_k = right vectors)
+// Multi-GPU: rows are sharded; each SpMM is preceded by an all-gather of the block's row shards
+// and each Gram matrix is all-reduced (b x b fp64).
+#include "common.cuh"
+#include "nccl_api.h"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+
+namespace gemb {
+
+struct HopeWork {
+    gemb_graph *g;
+    gemb_ctx *c;
+    int b;
+    int64_t rows;    // n_local
+    int64_t shard;   // n_shard (buffer rows)
+    float *buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // n_shard x b each
+    float *full = nullptr;   // n_pad x b (multi-GPU all-gather target)
+    double *G = nullptr, *G2 = nullptr, *w = nullptr, *Z = nullptr, *Zs = nullptr, *scal = nullptr;
+    float *Minv = nullptr, *M1 = nullptr, *M2 = nullptr;
+    int *rank_dev = nullptr;
+    int64_t spmm_wide = 0, spmm_all = 0;
+    ~HopeWork() {
+        for (auto p : buf) cudaFree(p);
+        cudaFree(full); cudaFree(G); cudaFree(G2); cudaFree(w); cudaFree(Z); cudaFree(Zs); cudaFree(scal);
+        cudaFree(Minv); cudaFree(M1); cudaFree(M2); cudaFree(rank_dev);
+    }
+};
+
+static int comm_allgather(HopeWork &W, const float *shard_src, int width) {
+    NcclApi *api = nccl_api();
+    if (!api) return GEMB_ERR_NCCL;
+    GEMB_TRY(W.c->t_comm.begin(W.c->stream));
+    ncclResult_t r = api->AllGather(shard_src, W.full, (size_t)W.shard * width, ncclFloat,
+                                    (ncclComm_t)W.c->comm, W.c->stream);
+    if (r != ncclSuccess) { set_error("ncclAllGather: %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
+    GEMB_TRY(W.c->t_comm.end(W.c->stream));
+    return GEMB_OK;
+}
+
+static int comm_allreduce_f64(HopeWork &W, double *buf, size_t count) {
+    if (W.c->nranks == 1) return GEMB_OK;
+    NcclApi *api = nccl_api();
+    if (!api) return GEMB_ERR_NCCL;
+    GEMB_TRY(W.c->t_comm.begin(W.c->stream));
+    ncclResult_t r = api->AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)W.c->comm, W.c->stream);
+    if (r != ncclSuccess) { set_error("ncclAllReduce: %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
+    GEMB_TRY(W.c->t_comm.end(W.c->stream));
+    return GEMB_OK;
+}
+
+// Y(shard) = X0 + alpha * op(A) * X(shard) ; X is all-gathered first when sharded
+static int dist_spmm(HopeWork &W, bool transpose, int width, float alpha, const float *Xshard,
+                     const float *X0, float *Y, bool timed) {
+    const float *Xfull = Xshard;
+    if (W.c->nranks > 1) {
+        GEMB_TRY(comm_allgather(W, Xshard, width));
+        Xfull = W.full;
+    }
+    if (timed) GEMB_TRY(W.c->t_spmm.begin(W.c->stream));
+    GEMB_TRY(spmm_launch(W.c, transpose ? W.g->AT : W.g->A, W.rows, width, alpha, Xfull, X0, Y));
+    if (timed) { GEMB_TRY(W.c->t_spmm.end(W.c->stream)); W.spmm_wide++; }
+    W.spmm_all++;
+    return GEMB_OK;
+}
+
+// out = sum_{j=1..J} (beta op(A))^j in   (Horner: W_m = in + beta op(A) W_{m-1}); t1,t2 scratch
+static int katz(HopeWork &W, bool transpose, float beta, int J, const float *in, float *out,
+                float *t1, float *t2) {
+    const float *cur = in;
+    for (int m = 1; m <= J; m++) {
+        if (m < J) {
+            float *dst = (m & 1) ? t1 : t2;
+            GEMB_TRY(dist_spmm(W, transpose, W.b, beta, cur, in, dst, true));
+            cur = dst;
+        } else {
+            GEMB_TRY(dist_spmm(W, transpose, W.b, beta, cur, nullptr, out, true));
+        }
+    }
+    return GEMB_OK;
+}
+
+static int gram_full(HopeWork &W, const float *P, const float *Q, double *G) {
+    GEMB_TRY(W.c->t_dense.begin(W.c->stream));
+    GEMB_TRY(gram_launch(W.c, W.rows, P, W.b, Q, W.b, G));
+    GEMB_TRY(W.c->t_dense.end(W.c->stream));
+    GEMB_TRY(comm_allreduce_f64(W, G, (size_t)W.b * W.b));
+    return GEMB_OK;
+}
+
+// one CholeskyQR pass: dst = src * R^-1 with R^T R = G (G destroyed). G must hold src^T src.
+static int cholqr_pass(HopeWork &W, double *G, const float *src, float *dst) {
+    GEMB_TRY(W.c->t_dense.begin(W.c->stream));
+    GEMB_TRY(chol_inverse_launch(W.c, W.b, G, W.Minv, W.rank_dev));
+    GEMB_TRY(apply_launch(W.c, W.rows, src, W.b, W.Minv, W.b, W.b, dst, W.b));
+    GEMB_TRY(W.c->t_dense.end(W.c->stream));
+    return GEMB_OK;
+}
+
+// M1[i][j] = Z[i][b-k+j] * theta_j^(p1),  M2 likewise with p2   (theta ascending, top k)
+__global__ void ritz_maps_kernel(int b, int k, const double *__restrict__ w, const double *__restrict__ Z,
+                                 float *__restrict__ M1, float *__restrict__ M2, double p1, double p2) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b * k) return;
+    const int i = idx / k, j = idx - i * k;
+    const double wmax = w[b - 1];
+    const double th = w[b - k + j];
+    const double z = Z[(size_t)i * b + (b - k + j)];
+    double a = 0.0, c = 0.0;
+    if (th > 1e-28 * wmax && th > 0.0) { a = z * pow(th, p1); c = z * pow(th, p2); }
+    M1[idx] = (float)a;
+    M2[idx] = (float)c;
+}
+
+__global__ void sqrt_top_kernel(int b, int k, const double *__restrict__ w, float *__restrict__ sigma) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k) { const double th = w[b - k + j]; sigma[j] = (float)(th > 0.0 ? sqrt(th) : 0.0); }
+}
+
+// column sums of squares of (A - B): out[j] (fp64), n x b row-major
+__global__ void coldiff_sumsq_kernel(int64_t n, int b, const float *__restrict__ A, const float *__restrict__ B,
+                                     double *__restrict__ out) {
+    const int j = threadIdx.x % b;  // blockDim.x is a multiple of b
+    const int rpb = blockDim.x / b;
+    double acc = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * rpb + threadIdx.x / b; r < n; r += (int64_t)gridDim.x * rpb) {
+        const double d = (double)A[r * b + j] - (double)B[r * b + j];
+        acc += d * d;
+    }
+    atomicAdd(out + j, acc);
+}
+
+}  // namespace gemb
+
+using namespace gemb;
+
+extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts *uo, float *X_out,
+                         float *sigma_out, gemb_hope_stats *stats) {
+    GEMB_ARG(g != nullptr, "graph");
+    GEMB_ARG(d >= 2 && d % 2 == 0, "d must be even and >= 2");
+    GEMB_ARG(!stats || stats->struct_size == sizeof(gemb_hope_stats), "stats.struct_size");
+    gemb_ctx *c = g->ctx;
+    GEMB_CUDA(cudaSetDevice(c->device));
+    gemb_hope_opts o;
+    memset(&o, 0, sizeof o);
+    o.oversample = 16; o.max_iters = 30; o.min_iters = 2; o.tol = 1e-6f; o.katz_terms = 0;
+    o.katz_tol = 1e-7f; o.seed = 1234; o.compute_residual = 0; o.verbose = 0;
+    if (uo) {
+        GEMB_ARG(uo->struct_size == sizeof(gemb_hope_opts), "opts.struct_size");
+        if (uo->oversample >= 0) o.oversample = uo->oversample;
+        if (uo->max_iters > 0) o.max_iters = uo->max_iters;
+        if (uo->min_iters > 0) o.min_iters = uo->min_iters;
+        if (uo->tol > 0) o.tol = uo->tol;
+        if (uo->katz_terms > 0) o.katz_terms = uo->katz_terms;
+        if (uo->katz_tol > 0) o.katz_tol = uo->katz_tol;
+        if (uo->seed) o.seed = uo->seed;
+        o.compute_residual = uo->compute_residual;
+        o.verbose = uo->verbose;
+    }
+    const int k = d / 2;
+    GEMB_ARG((int64_t)k <= g->n, "d/2 must not exceed the number of nodes");
+    int64_t bb = std::min<int64_t>(g->n, (int64_t)k + o.oversample);
+    int b = (int)((bb + 3) / 4 * 4);
+    GEMB_ARG(b <= 1024, "block width d/2 + oversample must be <= 1024");
+
+    HopeWork W;
+    W.g = g; W.c = c; W.b = b; W.rows = g->n_local; W.shard = g->n_shard;
+    const size_t blk = sizeof(float) * (size_t)W.shard * b;
+    for (int i = 0; i < 5; i++) {
+        GEMB_CUDA(cudaMalloc(&W.buf[i], blk ? blk : 4));
+        GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));  // padded rows stay 0
+    }
+    if (c->nranks > 1) GEMB_CUDA(cudaMalloc(&W.full, sizeof(float) * (size_t)g->n_pad * b));
+    GEMB_CUDA(cudaMalloc(&W.G, sizeof(double) * b * b));
+    GEMB_CUDA(cudaMalloc(&W.G2, sizeof(double) * b * b));
+    GEMB_CUDA(cudaMalloc(&W.Z, sizeof(double) * b * b));
+    GEMB_CUDA(cudaMalloc(&W.Zs, sizeof(double) * b * b));
+    GEMB_CUDA(cudaMalloc(&W.w, sizeof(double) * b));
+    GEMB_CUDA(cudaMalloc(&W.scal, sizeof(double) * (b + 8)));
+    GEMB_CUDA(cudaMalloc(&W.Minv, sizeof(float) * b * b));
+    GEMB_CUDA(cudaMalloc(&W.M1, sizeof(float) * b * b));
+    GEMB_CUDA(cudaMalloc(&W.M2, sizeof(float) * b * b));
+    GEMB_CUDA(cudaMalloc(&W.rank_dev, sizeof(int)));
+
+    c->t_spmm.reset(); c->t_dense.reset(); c->t_comm.reset(); c->t_misc.reset();
+    cudaEvent_t ev0, ev1;
+    GEMB_CUDA(cudaEventCreate(&ev0));
+    GEMB_CUDA(cudaEventCreate(&ev1));
+    GEMB_CUDA(cudaEventRecord(ev0, c->stream));
+
+    float *V = W.buf[0], *U = W.buf[1], *Wk = W.buf[2], *T1 = W.buf[3], *T2 = W.buf[4];
+    float norm2 = 0.f;
+    int J = o.katz_terms;
+
+    // ---- ||A||_2 by power iteration on A^T A with a 4-column block (only when J is automatic)
+    if (J <= 0) {
+        const int pw = 4;
+        float *x = T1, *y = T2, *z = Wk;  // reuse (width 4 slices of the big buffers)
+        GEMB_TRY(randn_launch(c, W.rows, pw, o.seed ^ 0x5bd1e995u, (uint64_t)g->row0, x));
+        double est = 0.0, prev = -1.0;
+        for (int it = 0; it < 16; it++) {
+            double h[2];
+            GEMB_TRY(sumsq_launch(c, W.rows * pw, x, W.scal));
+            const float *xf = x;
+            if (c->nranks > 1) {
+                // shard stride for width-4 gather = n_shard * 4 floats
+                NcclApi *api = nccl_api();
+                if (!api) return GEMB_ERR_NCCL;
+                ncclResult_t r = api->AllGather(x, W.full, (size_t)W.shard * pw, ncclFloat, (ncclComm_t)c->comm, c->stream);
+                if (r != ncclSuccess) { set_error("ncclAllGather: %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
+                xf = W.full;
+            }
+            GEMB_TRY(spmm_launch(c, g->A, W.rows, pw, 1.f, xf, nullptr, y));
+            const float *yf = y;
+            if (c->nranks > 1) {
+                NcclApi *api = nccl_api();
+                ncclResult_t r = api->AllGather(y, W.full, (size_t)W.shard * pw, ncclFloat, (ncclComm_t)c->comm, c->stream);
+                if (r != ncclSuccess) { set_error("ncclAllGather: %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
+                yf = W.full;
+            }
+            GEMB_TRY(spmm_launch(c, g->AT, W.rows, pw, 1.f, yf, nullptr, z));
+            W.spmm_all += 2;
+            GEMB_TRY(sumsq_launch(c, W.rows * pw, z, W.scal + 1));
+            GEMB_TRY(comm_allreduce_f64(W, W.scal, 2));
+            GEMB_CUDA(cudaMemcpyAsync(h, W.scal, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+            GEMB_CUDA(cudaStreamSynchronize(c->stream));
+            if (!(h[0] > 0.0) || !(h[1] > 0.0)) { est = 0.0; break; }  // A^T A x = 0: nilpotent-ish / empty
+            est = sqrt(sqrt(h[1] / h[0]));   // ||A^T A x|| / ||x|| -> sigma_max^2
+            GEMB_TRY(scale_launch(c, W.rows * pw, (float)(1.0 / sqrt(h[1])), z));
+            std::swap(x, z);
+            if (prev > 0 && fabs(est - prev) <= 1e-3 * est && it >= 3) break;
+            prev = est;
+        }
+        norm2 = (float)est;
+        const double x1 = (double)beta * est * 1.02;
+        if (x1 >= 1.0) {
+            set_error("beta * ||A||_2 = %.4g >= 1: the Katz series (I - beta A)^-1 beta A does not converge; "
+                      "choose beta < %.4g", (double)beta * est, 1.0 / est);
+            cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+            return GEMB_ERR_DIVERGE;
+        }
+        if (x1 <= 1e-30) J = 1;
+        else J = (int)ceil(log((double)o.katz_tol) / log(x1));
+        // a nilpotent A (e.g. a DAG) can have ||A||_2 large but finite series; the bound still holds
+        J = std::max(1, std::min(J, 4096));
+        // buffers were used as scratch with width 4: re-zero the touched prefixes (padding rows)
+        for (int i = 2; i < 5; i++) GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));
+    }
+
+    // ---- start block
+    GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)g->row0, T1));
+    GEMB_TRY(gram_full(W, T1, T1, W.G));
+    GEMB_TRY(cholqr_pass(W, W.G, T1, T2));
+    GEMB_TRY(gram_full(W, T2, T2, W.G));
+    GEMB_TRY(cholqr_pass(W, W.G, T2, V));
+
+    std::vector<double> theta(b), theta_prev(b, 0.0);
+    int iters = 0, converged = 0;
+    double change = 0.0;
+    for (int it = 1; it <= o.max_iters; it++) {
+        iters = it;
+        GEMB_TRY(katz(W, false, beta, J, V, U, T1, T2));              // U = S V
+        GEMB_TRY(gram_full(W, U, U, W.G));                            // T = U^T U
+        GEMB_CUDA(cudaMemcpyAsync(W.G2, W.G, sizeof(double) * b * b, cudaMemcpyDeviceToDevice, c->stream));
+        GEMB_TRY(c->t_dense.begin(c->stream));
+        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs));
+        GEMB_TRY(c->t_dense.end(c->stream));
+        GEMB_CUDA(cudaMemcpyAsync(theta.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        const double tmax = std::max(theta[b - 1], 1e-300);
+        change = 0.0;
+        for (int j = b - k; j < b; j++) change = std::max(change, fabs(theta[j] - theta_prev[j]) / tmax);
+        theta_prev = theta;
+        if (o.verbose)
+            fprintf(stderr, "[gemb_hope] it %d  sigma_max %.6g sigma_k %.6g  ritz change %.3g\n", it,
+                    sqrt(tmax), sqrt(std::max(theta[b - k], 0.0)), change);
+        if (it >= o.min_iters && change <= (double)o.tol) { converged = 1; break; }
+        if (it == o.max_iters) break;
+        GEMB_TRY(cholqr_pass(W, W.G, U, T1));                         // T1 = orth(U) (one pass)
+        GEMB_TRY(katz(W, true, beta, J, T1, Wk, U, T2));              // Wk = S^T T1   (U is scratch now)
+        GEMB_TRY(gram_full(W, Wk, Wk, W.G));
+        GEMB_TRY(cholqr_pass(W, W.G, Wk, T1));
+        GEMB_TRY(gram_full(W, T1, T1, W.G));
+        GEMB_TRY(cholqr_pass(W, W.G, T1, V));                         // V = orth(S^T orth(S V))
+    }
+
+    // ---- extraction: X = [U Z_k theta^-1/4 | V Z_k theta^1/4]; U = S V (un-normalised), V orthonormal
+    float *Xd = T1;  // n_shard x d fits: d = 2k <= ... ensure capacity
+    float *Xalloc = nullptr;
+    if ((size_t)d > (size_t)b) {
+        GEMB_CUDA(cudaMalloc(&Xalloc, sizeof(float) * (size_t)std::max<int64_t>(W.rows, 1) * d));
+        Xd = Xalloc;
+    }
+    GEMB_TRY(c->t_dense.begin(c->stream));
+    ritz_maps_kernel<<<(b * k + 255) / 256, 256, 0, c->stream>>>(b, k, W.w, W.Z, W.M1, W.M2, -0.25, 0.25);
+    GEMB_CUDA(cudaGetLastError());
+    GEMB_TRY(apply_launch(c, W.rows, U, b, W.M1, k, k, Xd, d));
+    GEMB_TRY(apply_launch(c, W.rows, V, b, W.M2, k, k, Xd + k, d));
+    float *sig_dev = (float *)W.Minv;  // reuse
+    sqrt_top_kernel<<<(k + 127) / 128, 128, 0, c->stream>>>(b, k, W.w, sig_dev);
+    GEMB_CUDA(cudaGetLastError());
+    GEMB_TRY(c->t_dense.end(c->stream));
+
+    float resid_max = -1.f;
+    if (o.compute_residual) {
+        // left vectors P = U Z theta^-1/2 (all b Ritz pairs), right Q = V Z ; check S^T P = Q sigma
+        ritz_maps_kernel<<<(b * b + 255) / 256, 256, 0, c->stream>>>(b, b, W.w, W.Z, W.M1, W.M2, -0.5, 0.5);
+        GEMB_CUDA(cudaGetLastError());
+        float *Pm = Wk, *Qs = (Xalloc ? T1 : nullptr);
+        float *Qalloc = nullptr;
+        if (!Qs) { GEMB_CUDA(cudaMalloc(&Qalloc, blk ? blk : 4)); GEMB_CUDA(cudaMemsetAsync(Qalloc, 0, blk, c->stream)); Qs = Qalloc; }
+        GEMB_TRY(apply_launch(c, W.rows, U, b, W.M1, b, b, Pm, b));          // P
+        GEMB_TRY(apply_launch(c, W.rows, V, b, W.M2, b, b, Qs, b));          // Q sigma  (theta^1/2 = sigma)
+        // S^T P -> needs scratch: U is still needed? (X already extracted) -> reuse U and T2
+        float *STP = nullptr;
+        GEMB_CUDA(cudaMalloc(&STP, blk ? blk : 4));
+        GEMB_CUDA(cudaMemsetAsync(STP, 0, blk, c->stream));
+        float *scr1 = U, *scr2 = T2;
+        int s = katz(W, true, beta, J, Pm, STP, scr1, scr2);
+        if (s != GEMB_OK) { cudaFree(STP); cudaFree(Qalloc); cudaFree(Xalloc); return s; }
+        GEMB_CUDA(cudaMemsetAsync(W.scal, 0, sizeof(double) * b, c->stream));
+        const int threads = (256 / b) * b > 0 ? (256 / b) * b : b;
+        coldiff_sumsq_kernel<<<c->sm_count * 4, threads, 0, c->stream>>>(W.rows, b, STP, Qs, W.scal);
+        GEMB_CUDA(cudaGetLastError());
+        GEMB_TRY(comm_allreduce_f64(W, W.scal, b));
+        std::vector<double> rs(b);
+        GEMB_CUDA(cudaMemcpyAsync(rs.data(), W.scal, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        const double smax = sqrt(std::max(theta[b - 1], 1e-300));
+        double rm = 0.0;
+        for (int j = b - k; j < b; j++) rm = std::max(rm, sqrt(rs[j]) / smax);
+        resid_max = (float)rm;
+        cudaFree(STP);
+        cudaFree(Qalloc);
+    }
+
+    GEMB_CUDA(cudaEventRecord(ev1, c->stream));
+    GEMB_CUDA(cudaEventSynchronize(ev1));
+    float total_ms = 0.f;
+    GEMB_CUDA(cudaEventElapsedTime(&total_ms, ev0, ev1));
+
+    double d2h_ms = 0.0;
+    if (X_out || sigma_out) {
+        cudaEvent_t e2, e3;
+        GEMB_CUDA(cudaEventCreate(&e2)); GEMB_CUDA(cudaEventCreate(&e3));
+        GEMB_CUDA(cudaEventRecord(e2, c->stream));
+        if (X_out) GEMB_CUDA(cudaMemcpyAsync(X_out, Xd, sizeof(float) * (size_t)W.rows * d, cudaMemcpyDeviceToHost, c->stream));
+        if (sigma_out) GEMB_CUDA(cudaMemcpyAsync(sigma_out, sig_dev, sizeof(float) * k, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaEventRecord(e3, c->stream));
+        GEMB_CUDA(cudaEventSynchronize(e3));
+        float ms = 0.f; cudaEventElapsedTime(&ms, e2, e3); d2h_ms = ms;
+        cudaEventDestroy(e2); cudaEventDestroy(e3);
+    }
+    cudaFree(Xalloc);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+
+    if (stats) {
+        stats->iters = iters;
+        stats->katz_terms = J;
+        stats->block = b;
+        stats->converged = converged;
+        stats->spmm_count = W.spmm_wide;   /* block-width sweeps (norm estimation excluded) */
+        stats->spmm_ms = c->t_spmm.total_ms();
+        const double nnz = (double)g->A.nnz;
+        stats->spmm_bytes = (g->A.data ? 8.0 : 4.0) * nnz + 4.0 * (double)(W.rows + 1) +
+                            4.0 * (double)b * ((double)g->n + (double)W.rows);
+        stats->dense_ms = c->t_dense.total_ms();
+        stats->comm_ms = c->t_comm.total_ms();
+        stats->total_ms = total_ms;
+        stats->h2d_ms = 0.0;
+        stats->d2h_ms = d2h_ms;
+        stats->norm2_A = norm2;
+        stats->ritz_change = (float)change;
+        stats->resid_max = resid_max;
+    }
+    return GEMB_OK;
+}

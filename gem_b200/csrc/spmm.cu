@@ -1,0 +1,129 @@
+// gem_b200/csrc/spmm.cu -- CSR SpMM  Y = X0 + alpha * A * X  over an fp32 row-major block.
+//
+// Replaces the dense products hidden in hope.py:31 (inv(I - beta A) . beta A) and inside
+// scipy's svds matvecs (hope.py:33): S is never formed, every S.x is a Horner sweep of this kernel.
+//
+// Mapping (HBM/L2-bound gather): a group of G = b/4 threads owns one CSR row; thread
+// c of the group owns columns [4c, 4c+4) of the block, so one nonzero = one coalesced 16*G-byte
+// read of X[col, :] (320 B for b = 80) and the accumulators never leave registers.  Column ids and
+// values of a row are read through the read-only path (same address across the group -> one L1
+// broadcast).  The nonzero loop is unrolled by 4 so that each thread keeps 4 independent 16-byte
+// gathers in flight.  The Horner epilogue (X0 + alpha * acc) is fused: one extra coalesced read.
+#include "common.cuh"
+
+namespace gemb {
+
+__device__ __forceinline__ void fma4(float4 &a, float v, const float4 &x) {
+    a.x = fmaf(v, x.x, a.x);
+    a.y = fmaf(v, x.y, a.y);
+    a.z = fmaf(v, x.z, a.z);
+    a.w = fmaf(v, x.w, a.w);
+}
+
+template <bool HAS_VAL, bool HAS_X0>
+__global__ void __launch_bounds__(256)
+spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                     const float *__restrict__ vals, int64_t n_rows, int G, int rows_per_cta,
+                     float alpha, const float4 *__restrict__ X, const float4 *__restrict__ X0,
+                     float4 *__restrict__ Y) {
+    const int tid = threadIdx.x;
+    const int lr = tid / G;
+    const int c = tid - lr * G;
+    if (lr >= rows_per_cta) return;
+    const int64_t row = (int64_t)blockIdx.x * rows_per_cta + lr;
+    if (row >= n_rows) return;
+    const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+    const float4 *Xc = X + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i = s;
+    for (; i + 4 <= e; i += 4) {
+        const int c0 = __ldg(indices + i), c1 = __ldg(indices + i + 1);
+        const int c2 = __ldg(indices + i + 2), c3 = __ldg(indices + i + 3);
+        float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
+        if (HAS_VAL) {
+            v0 = __ldg(vals + i);
+            v1 = __ldg(vals + i + 1);
+            v2 = __ldg(vals + i + 2);
+            v3 = __ldg(vals + i + 3);
+        }
+        const float4 x0 = __ldg(Xc + (int64_t)c0 * G);
+        const float4 x1 = __ldg(Xc + (int64_t)c1 * G);
+        const float4 x2 = __ldg(Xc + (int64_t)c2 * G);
+        const float4 x3 = __ldg(Xc + (int64_t)c3 * G);
+        fma4(acc, v0, x0);
+        fma4(acc, v1, x1);
+        fma4(acc, v2, x2);
+        fma4(acc, v3, x3);
+    }
+    for (; i < e; i++) {
+        const int c0 = __ldg(indices + i);
+        const float v0 = HAS_VAL ? __ldg(vals + i) : 1.f;
+        const float4 x0 = __ldg(Xc + (int64_t)c0 * G);
+        fma4(acc, v0, x0);
+    }
+    float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+    if (HAS_X0) {
+        const float4 z = __ldg(X0 + row * G + c);
+        r.x += z.x;
+        r.y += z.y;
+        r.z += z.z;
+        r.w += z.w;
+    }
+    Y[row * G + c] = r;
+}
+
+int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha,
+                const float *X, const float *X0, float *Y) {
+    GEMB_ARG(b > 0 && b % 4 == 0 && b <= 1024, "block width must be a multiple of 4, <= 1024");
+    if (n_rows == 0) return GEMB_OK;
+    const int G = b / 4;
+    const int rows_per_cta = 256 / G;
+    const int64_t grid = (n_rows + rows_per_cta - 1) / rows_per_cta;
+    GEMB_ARG(grid < (int64_t)2147483647, "grid too large");
+    dim3 g((unsigned)grid), t(256);
+    const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0;
+    float4 *Y4 = (float4 *)Y;
+#define LAUNCH(V, Z)                                                                              \
+    spmm_rowgroup_kernel<V, Z><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G,  \
+                                                         rows_per_cta, alpha, X4, X04, Y4)
+    if (A.data) {
+        if (X0) LAUNCH(true, true); else LAUNCH(true, false);
+    } else {
+        if (X0) LAUNCH(false, true); else LAUNCH(false, false);
+    }
+#undef LAUNCH
+    GEMB_CUDA(cudaGetLastError());
+    return GEMB_OK;
+}
+
+}  // namespace gemb
+
+using namespace gemb;
+
+extern "C" int gemb_spmm(gemb_graph *g, int transpose, int b, float alpha, const float *X,
+                         const float *X0, float *Y) {
+    GEMB_ARG(g && X && Y, "graph/X/Y");
+    GEMB_ARG(b > 0 && b % 4 == 0, "b must be a positive multiple of 4");
+    gemb_ctx *c = g->ctx;
+    GEMB_CUDA(cudaSetDevice(c->device));
+    float *dX = nullptr, *dX0 = nullptr, *dY = nullptr;
+    const size_t full = sizeof(float) * (size_t)g->n * b, shard = sizeof(float) * (size_t)g->n_local * b;
+    GEMB_CUDA(cudaMalloc(&dX, full ? full : 4));
+    GEMB_CUDA(cudaMalloc(&dY, shard ? shard : 4));
+    if (X0) GEMB_CUDA(cudaMalloc(&dX0, shard ? shard : 4));
+    GEMB_CUDA(cudaMemcpyAsync(dX, X, full, cudaMemcpyHostToDevice, c->stream));
+    if (X0) GEMB_CUDA(cudaMemcpyAsync(dX0, X0, shard, cudaMemcpyHostToDevice, c->stream));
+    int s = spmm_launch(c, transpose ? g->AT : g->A, g->n_local, b, alpha, dX, dX0, dY);
+    if (s == GEMB_OK) {
+        cudaError_t e = cudaMemcpyAsync(Y, dY, shard, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            set_error("gemb_spmm: %s", cudaGetErrorString(e));
+            s = GEMB_ERR_CUDA;
+        }
+    }
+    cudaFree(dX);
+    cudaFree(dY);
+    cudaFree(dX0);
+    return s;
+}

@@ -1,0 +1,169 @@
+/*
+ * include/gemb200.h -- C ABI of libgemb200.so, the B200 (sm_100a) core behind GEM's
+ * StaticGraphEmbedding plugin API for HOPE and node2vec.
+ *
+ * The reference has no FFI for this path: HOPE is four NumPy/SciPy lines
+ * (gem/embedding/hope.py:28-36) and node2vec is an argv + text-file hand-off to a prebuilt
+ * SNAP executable (gem/embedding/node2vec.py:31-53).  Each entry point below names the reference
+ * interface it replaces; INTEGRATION.md shows the ctypes stub a GEM maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 (GEMB_OK) or a negative
+ *     gemb_status; gemb_last_error() gives the message of the last failure on this thread.
+ *   - the caller owns every host buffer; the library owns device memory behind opaque handles.
+ *   - calls are blocking; one gemb_ctx is bound to one CUDA device and is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     GEMB_ERR_CUDA.
+ *   - matrices are row-major; node ids / column ids are int32; CSR offsets are int64 on the
+ *     host ABI (node2vec) or int32 (HOPE shards, nnz < 2^31 per shard).
+ */
+#ifndef GEMB200_H
+#define GEMB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEMB_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    GEMB_OK = 0,
+    GEMB_ERR_CUDA = -1,      /* no device / CUDA runtime or kernel failure */
+    GEMB_ERR_ARG = -2,       /* bad argument */
+    GEMB_ERR_NOMEM = -3,     /* host or device allocation failed */
+    GEMB_ERR_DIVERGE = -4,   /* beta * ||A||_2 >= 1: Katz series does not converge */
+    GEMB_ERR_NCCL = -5,      /* NCCL missing or collective failed */
+    GEMB_ERR_UNSUPPORTED = -6
+} gemb_status;
+
+typedef struct gemb_ctx gemb_ctx;     /* one CUDA device + stream (+ optional NCCL communicator) */
+typedef struct gemb_graph gemb_graph; /* a CSR row shard (and its transpose) resident in HBM   */
+
+int gemb_version(void);
+const char *gemb_last_error(void);
+int gemb_device_count(void); /* number of CUDA devices, 0 if none / no driver */
+
+int gemb_ctx_create(int device, gemb_ctx **out);
+int gemb_ctx_destroy(gemb_ctx *ctx);
+
+/* Pinned (page-locked) host buffers for the host<->device copies of the e2e path. */
+int gemb_host_alloc(size_t bytes, void **out);
+int gemb_host_free(void *p);
+
+/* ---- multi-GPU: one process per GPU; rank 0 makes the id, every rank calls init.
+ * (No reference counterpart: GEM is single-process) */
+#define GEMB_UNIQUE_ID_BYTES 128
+int gemb_comm_unique_id(void *id_out /* GEMB_UNIQUE_ID_BYTES */);
+int gemb_comm_init(gemb_ctx *ctx, int rank, int nranks, const void *id);
+
+/* ---- graph upload.
+ * Replaces: nx.to_numpy_matrix(graph) (hope.py:28) and the text edge list written by
+ * graph_util.saveGraphToEdgeListTxtn2v (graph_util.py:137-140) + SNAP ReadGraph (bin@0x406550).
+ *
+ * The shard holds rows [row0, row0+n_local) of the n x n adjacency A in CSR form with GLOBAL
+ * column ids, and the same row range of A^T (pass indptr_t == NULL when A is symmetric: A^T = A).
+ * data / data_t may be NULL (all weights 1.0).  Single GPU: row0 = 0, n_local = n.
+ * Multi GPU (after gemb_comm_init): every rank must use n_local = ceil(n / nranks) rows
+ * (the last rank may own fewer real rows; pass what it has, the library pads).  */
+int gemb_graph_upload(gemb_ctx *ctx, int64_t n, int64_t row0, int64_t n_local,
+                      const int32_t *indptr, const int32_t *indices, const float *data,
+                      const int32_t *indptr_t, const int32_t *indices_t, const float *data_t,
+                      gemb_graph **out);
+int gemb_graph_free(gemb_graph *g);
+
+/* Test hook for the dominant kernel:  Y = X0 + alpha * op(A) * X   (X0 may be NULL).
+ * X is the full n x b block, X0 and Y are the n_local x b row shards; all HOST, row-major fp32.
+ * b must be a multiple of 4. */
+int gemb_spmm(gemb_graph *g, int transpose, int b, float alpha, const float *X, const float *X0,
+              float *Y);
+
+/* ---- HOPE.  Replaces hope.py:29-36: S = (I - beta A)^-1 beta A is never formed; its top
+ * k = d/2 singular triplets come from a block subspace iteration with Rayleigh-Ritz whose
+ * operator applications are Katz/Horner sweeps of CSR SpMM.  Output convention = the reference:
+ * X = [U sqrt(Sigma) | V sqrt(Sigma)], sigma ASCENDING (scipy svds order). */
+typedef struct {
+    uint32_t struct_size;  /* = sizeof(gemb_hope_opts) */
+    int32_t oversample;    /* extra block columns, default 16 (block b = min(n, d/2 + oversample)) */
+    int32_t max_iters;     /* max subspace iterations, default 30 */
+    int32_t min_iters;     /* default 2 */
+    float tol;             /* stop when max_j |theta_j - theta_j_prev| <= tol * theta_max over the top
+                              k Ritz values theta = sigma^2; default 1e-6 */
+    int32_t katz_terms;    /* Horner terms J; 0 = choose so that (beta*||A||_2)^J <= katz_tol */
+    float katz_tol;        /* default 1e-7 */
+    uint64_t seed;         /* start block, default 1234 */
+    int32_t compute_residual; /* 1: one extra Katz application to report ||S^T u - sigma v|| */
+    int32_t verbose;
+} gemb_hope_opts;
+
+typedef struct {
+    uint32_t struct_size;
+    int32_t iters;         /* subspace iterations performed */
+    int32_t katz_terms;    /* J actually used */
+    int32_t block;         /* b */
+    int32_t converged;
+    int64_t spmm_count;    /* SpMM sweeps executed (all of width `block` except norm estimation) */
+    double spmm_ms;        /* sum of CUDA-event durations of the block-width SpMM launches */
+    double spmm_bytes;     /* algorithmic bytes of ONE block-width sweep: 8*nnz + 4*(n+1) + 8*n*b
+                              (4*nnz less when the shard is unweighted) */
+    double dense_ms;       /* Gram + apply + small factorizations */
+    double comm_ms;        /* NCCL time (multi-GPU) */
+    double total_ms;       /* device time of the whole call (events), excluding H2D/D2H */
+    double h2d_ms, d2h_ms;
+    float norm2_A;         /* estimated ||A||_2 */
+    float ritz_change;     /* last max relative Ritz-value change */
+    float resid_max;       /* max_j ||S^T u_j - sigma_j v_j|| / sigma_max (compute_residual=1) */
+} gemb_hope_stats;
+
+/* X_out: n_local x d host buffer, or NULL to leave the result on the device (bench `value`).
+ * sigma_out: d/2 floats (ascending) or NULL. */
+int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts *opts, float *X_out,
+              float *sigma_out, gemb_hope_stats *stats);
+
+/* ---- node2vec.  Replaces the SNAP executable GEM shells out to (node2vec.py:31-48):
+ * PreprocessTransitionProbs (bin@0x4127f0), node2vec() walks (bin@0x40c420),
+ * LearnEmbeddings/TrainModel (bin@0x40ea30 / 0x40d6a0), WriteOutput + loadEmbedding
+ * (graph_util.py:161-169).  Only p = q = 1 (first-order tables) is implemented on the GPU;
+ * other values return GEMB_ERR_UNSUPPORTED.
+ *
+ * The graph must be uploaded single-GPU style (row0 = 0, n_local = n) with every row's column
+ * ids sorted ascending (SNAP adjacency order).  weights64: fp64 edge weights in CSR order or
+ * NULL for 1.0 (the reference parses the "%f" text into doubles; alias tables are built in fp64
+ * so that walks are bit-exact against oracle/n2v_oracle.c). */
+int gemb_n2v_alias(gemb_graph *g, const double *weights64, int32_t *K_out /* nnz */,
+                   double *U_out /* nnz */);
+
+typedef struct {
+    uint32_t struct_size;
+    double alias_ms, shuffle_ms, walk_ms, vocab_ms, sgns_ms, total_ms, h2d_ms, d2h_ms, comm_ms;
+    int64_t n_tokens;      /* vocabulary size V (includes the phantom token 0 if walks were padded) */
+    int64_t n_walks;       /* walks generated by this rank */
+    int64_t pairs;         /* (centre, context) pairs trained by this rank */
+    double sgns_bytes;     /* algorithmic bytes: pairs * 14 rows * 4*d */
+    double walk_bytes;     /* 24 B per transition */
+} gemb_n2v_stats;
+
+/* Walks only (parity hook).  nids: the N start nodes in SNAP node-table order (first appearance
+ * in the edge list).  seed: the TRnd seed (the binary uses time(NULL)).  Walk w = i*N + j
+ * (round i, shuffled position j) reads the Park-Miller stream at offset
+ * (i+1)*(N-1) + w*(2*walk_len-3)  -- identical to the single-threaded binary whenever no walk
+ * hits a dead end (oracle mode 1).  Walks [w_begin, w_end) are generated;
+ * walks_out: (w_end-w_begin) x walk_len int32 host buffer (zero padded after a dead end). */
+int gemb_n2v_walks(gemb_graph *g, const double *weights64, const int32_t *nids, int64_t N,
+                   int walk_len, int num_walks, double p, double q, int32_t seed, int64_t w_begin,
+                   int64_t w_end, int32_t *walks_out, gemb_n2v_stats *stats);
+
+/* Full pipeline.  X_out: n_rows x d host fp32 (row = node id, like loadEmbedding; rows of ids
+ * that never appear stay 0) or NULL.  sequential != 0 trains with ONE warp consuming the single
+ * TRnd(seed) stream in program order (parity mode: follows oracle/n2v_oracle.c up to fp32
+ * rounding); sequential == 0 is the Hogwild production mode. */
+int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, int64_t N, int d,
+                  int walk_len, int num_walks, int con_size, int max_iter, double p, double q,
+                  int32_t seed, int sequential, int64_t n_rows, float *X_out,
+                  gemb_n2v_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMB200_H */

@@ -1,0 +1,99 @@
+"""Host-side mirror of the reference plugin API (reference tests/test_embedding_classes.py:37-48 style)
+and of the graph ingestion.  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_karate_nx
+
+
+def test_embedding_class_contract():
+    # reference tests/test_embedding_classes.py:37-48
+    from gem_b200.embedding.hope import HOPE
+    from gem_b200.embedding.node2vec import node2vec
+    for cls, name in ((HOPE, 'hope_gsvd'), (node2vec, 'node2vec_rw')):
+        model = cls()
+        with pytest.raises(ValueError, match='graph needed'):
+            model.learn_embedding()
+        assert model.hyper_params['method_name'] == model.get_method_name() == name
+        with pytest.raises(ValueError, match='Embedding not learned yet'):
+            model.get_embedding()
+    import networkx as nx
+    with pytest.raises(ValueError, match='graph needed'):
+        HOPE(d=4, beta=0.01).learn_embedding(graph=nx.DiGraph())      # empty graph is falsy (hope.py:25)
+    m = HOPE(d=4, beta=0.01)
+    assert m.get_method_summary() == 'hope_gsvd_4'
+    m2 = node2vec(d=2, max_iter=1, walk_len=80, num_walks=10, con_size=10, ret_p=1, inout_p=1, data_set='sbm')
+    assert m2._walk_len == 80 and m2._data_set == 'sbm' and m2.get_method_summary() == 'node2vec_rw_2'
+
+
+def test_hyper_params_class_dict_semantics():
+    # kwargs update the CLASS dict, later instances inherit them (kept on purpose)
+    from gem_b200.embedding.hope import HOPE
+    saved = dict(HOPE.hyper_params)
+    try:
+        HOPE(d=6, beta=0.5)
+        assert HOPE()._d == 6
+    finally:
+        HOPE.hyper_params.clear()
+        HOPE.hyper_params.update(saved)
+
+
+def test_reconstructed_adj_matches_reference_loop():
+    from gem_b200.embedding.hope import HOPE
+    from gem_b200.embedding.node2vec import node2vec
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((7, 6))
+    for m in (HOPE(d=6, beta=0.1), node2vec(d=6)):
+        A = m.get_reconstructed_adj(X=X)
+        ref = np.zeros((7, 7))
+        for i in range(7):
+            for j in range(7):
+                if i != j:
+                    ref[i, j] = m.get_edge_weight(i, j)       # static_graph_embedding.py:59-64
+        assert np.allclose(A, ref) and np.all(np.diag(A) == 0)
+        assert m.get_embedding() is X                           # reference sets self._X = X (:56)
+
+
+def test_csr_from_networkx_matches_to_numpy_array():
+    import networkx as nx
+    from gem_b200 import graph as hg
+    G = load_karate_nx()
+    csr = hg.from_networkx(G)
+    dense = nx.to_numpy_array(G, nodelist=list(G.nodes))
+    assert np.array_equal(csr.to_scipy().toarray(), dense)
+    assert csr.nodes == list(G.nodes) and csr.data is None     # unit weights are dropped
+    assert not csr.is_symmetric()
+    t = csr.transpose()
+    assert np.array_equal(t.to_scipy().toarray(), dense.T)
+    H = nx.DiGraph()
+    H.add_weighted_edges_from([(0, 1, 0.5), (1, 0, 0.5), (1, 2, 2.0), (2, 1, 2.0)])
+    c2 = hg.from_networkx(H)
+    assert c2.is_symmetric() and c2.data is not None
+
+
+def test_n2v_inputs_order_and_weights():
+    import networkx as nx
+    from gem_b200 import graph as hg
+    G = nx.DiGraph()
+    G.add_weighted_edges_from([(5, 2, 0.1234567), (2, 7, 1.0), (5, 7, 3.0)])
+    csr, nids = hg.n2v_inputs_from_networkx(G)
+    assert nids.tolist() == [5, 2, 7]                           # first appearance in the edge list
+    assert csr.n == 8 and csr.indices[csr.indptr[5]:csr.indptr[6]].tolist() == [2, 7]
+    assert csr.data[csr.indptr[5]] == float('%f' % 0.1234567)   # graph_util.py:140 writes %f
+    sh = csr.row_shard(1, 2)
+    assert sh[0] == 4 and sh[1][0] == 0
+
+
+def test_wire_formats_roundtrip(tmp_path):
+    from gem_b200.utils import graph_util
+    G = load_karate_nx()
+    f = str(tmp_path / 'g.txt')
+    graph_util.saveGraphToEdgeListTxtn2v(G, f)
+    lines = open(f).read().splitlines()
+    assert lines[0] == '0 31 1.000000' and len(lines) == G.number_of_edges()
+    G2 = graph_util.loadGraphFromEdgeListTxt(f, directed=True)
+    assert sorted(G2.edges()) == sorted(G.edges())
+    X = np.arange(12, dtype=np.float64).reshape(4, 3) / 7
+    e = str(tmp_path / 'x.emb')
+    graph_util.saveEmbedding(X, e, ids=[2, 0, 3, 1])
+    assert np.allclose(graph_util.loadEmbedding(e), X, rtol=1e-5)
