@@ -1,0 +1,114 @@
+"""HOPE parity on the GPU, through the reference-facing plugin class (gem_b200.embedding.hope.HOPE ->
+ctypes -> libgemb200.so).  Compared with
+  * the reference's own goldens (tests/golden/karate_HOPE.txt, sbm1024.npz:hope_golden) and the
+    reference-class outputs in tests/golden/ref_hope_*.npz,
+  * the fp64 oracle (oracle/hope_oracle.py) on the same inputs.
+Tolerances (fp32 arithmetic vs the reference's fp64): sigma 2e-5 relative, reconstruction
+||X1 X2^T - ref||_F/||ref||_F 2e-4, principal angle of the well separated part of the subspace 0.05 deg,
+|mean(target - X)| < 1e-3 (the reference's own bar, tests/test_sbm.py:94)."""
+import numpy as np
+import pytest
+
+from conftest import golden_path, load_karate_nx, load_sbm1024_nx, nx_from_npz
+
+pytestmark = pytest.mark.gpu
+
+SIG_RTOL = 2e-5
+RECON_TOL = 2e-4
+
+
+def _fresh_hope(**kw):
+    from gem_b200.embedding.hope import HOPE
+    HOPE.hyper_params.clear()
+    HOPE.hyper_params.update({'method_name': 'hope_gsvd'})
+    return HOPE(**kw)
+
+
+def test_karate_golden(gpu_ctx, hope_oracle):
+    ho = hope_oracle
+    G = load_karate_nx()
+    gold = np.loadtxt(golden_path('karate_HOPE.txt'))
+    m = _fresh_hope(d=4, beta=0.01, oversample=32, tol=1e-9, max_iters=60, compute_residual=1)
+    X = m.learn_embedding(graph=G, is_weighted=True, no_python=True)
+    assert X.shape == (34, 4) and m.get_embedding() is X
+    Xa = ho.align_pair_signs(X, gold)
+    assert np.allclose(Xa, gold, atol=2e-6), np.abs(Xa - gold).max()     # reference: np.allclose
+    sig = ho.sigma_from_embedding(gold)
+    assert np.allclose(m._sigma, sig, rtol=SIG_RTOL)
+    assert np.all(np.diff(m._sigma) >= 0)
+    assert m.stats['resid_max'] < 1e-4
+    # get_edge_weight / get_reconstructed_adj follow the reference (hope.py:43-44)
+    A = m.get_reconstructed_adj()
+    assert abs(A[3, 5] - np.dot(X[3, :2], X[5, 2:])) < 1e-7 and A[4, 4] == 0
+
+
+def test_sbm1024_golden(gpu_ctx, hope_oracle):
+    ho = hope_oracle
+    G, z = load_sbm1024_nx()
+    gold = z['hope_golden']
+    m = _fresh_hope(d=256, beta=0.01, oversample=128, tol=1e-9, max_iters=400, min_iters=8)
+    X = m.learn_embedding(graph=G, is_weighted=True, no_python=True)
+    assert abs(np.mean(gold - X)) < 1e-3                                   # tests/test_sbm.py:94
+    sg, sx = ho.sigma_from_embedding(gold), np.asarray(m._sigma, dtype=np.float64)
+    assert np.allclose(sx, sg, rtol=1e-4), np.abs(sx / sg - 1).max()
+    # top of the spectrum is well separated (3 communities): tight subspace check there
+    k = 128
+    U, Ug = X[:, :k], gold[:, :k]
+    assert ho.principal_angles_deg(U[:, -3:], Ug[:, -3:])[0] < 0.05
+    assert ho.recon_rel_err(X, gold) < 5e-2      # bulk singular values are nearly degenerate at the cut
+
+
+@pytest.mark.parametrize('name,recon_tol', [('karate_d16', RECON_TOL), ('sbm1024_d16', 2e-3),
+                                            ('randw200_d32', RECON_TOL)])
+def test_against_reference_class_outputs(gpu_ctx, hope_oracle, name, recon_tol):
+    ho = hope_oracle
+    z = np.load(golden_path('ref_hope_%s.npz' % name))
+    G = nx_from_npz(z)
+    d, beta, Xref = int(z['d']), float(z['beta']), z['X']
+    m = _fresh_hope(d=d, beta=beta, oversample=64, tol=1e-10, max_iters=300, min_iters=6, compute_residual=1)
+    X = m.learn_embedding(graph=G)
+    assert np.allclose(m._sigma, ho.sigma_from_embedding(Xref), rtol=SIG_RTOL, atol=1e-9)
+    assert ho.recon_rel_err(X, Xref) < recon_tol, ho.recon_rel_err(X, Xref)
+    assert m.stats['resid_max'] < 1e-3
+
+
+def test_repeated_singular_values_cliques(gpu_ctx, hope_oracle):
+    """Ring of cliques: exactly repeated sigma -> vectors are not unique; sigma and residuals are."""
+    ho = hope_oracle
+    z = np.load(golden_path('ref_hope_cliques_d24.npz'))
+    G = nx_from_npz(z)
+    m = _fresh_hope(d=24, beta=0.05, oversample=40, tol=1e-10, max_iters=200, compute_residual=1)
+    X = m.learn_embedding(graph=G)
+    assert np.allclose(m._sigma, ho.sigma_from_embedding(z['X']), rtol=SIG_RTOL)
+    A = ho.adjacency_from_nx(G)
+    r1, r2, _, _ = ho.svd_residuals(A, 0.05, X, ho.katz_terms_needed(A, 0.05, 1e-14))
+    assert max(r1.max(), r2.max()) < 2e-5
+
+
+def test_divergent_beta_fails_loudly(gpu_ctx):
+    G, _ = load_sbm1024_nx()
+    m = _fresh_hope(d=8, beta=0.5)
+    with pytest.raises(RuntimeError, match='Katz series'):
+        m.learn_embedding(graph=G)
+
+
+def test_large_sparse_input_properties(gpu_ctx, hope_oracle):
+    """SBM at 100k nodes through the CSR entry of the plugin; checked with size-independent properties:
+    ascending sigma, orthonormal U and V, SVD residuals of the fp64 matrix-free operator, and sigma
+    against the CPU sparse oracle (scipy svds on the same Katz operator)."""
+    from gem_b200 import synth
+    ho = hope_oracle
+    csr = synth.sbm(n=100_000, block=1000, seed=11)
+    m = _fresh_hope(d=16, beta=0.01, tol=1e-8, max_iters=100, min_iters=4, compute_residual=1)
+    X = m.learn_embedding(graph=csr)
+    sig = np.asarray(m._sigma, dtype=np.float64)
+    assert np.all(np.diff(sig) >= 0)
+    A = csr.to_scipy()
+    J = ho.katz_terms_needed(A, 0.01, 1e-12)
+    r1, r2, U, V = ho.svd_residuals(A, 0.01, X, J, sigma=sig)
+    assert np.abs(U.T @ U - np.eye(8)).max() < 1e-4 and np.abs(V.T @ V - np.eye(8)).max() < 1e-4
+    assert r1.max() < 5e-3 and r2.max() < 5e-3, (r1.max(), r2.max())
+    assert m.stats['resid_max'] < 5e-3
+    Xo, so, _ = ho.hope_sparse(A, 16, 0.01, tol=1e-6)
+    assert np.allclose(sig[-1], so[-1], rtol=1e-5)               # isolated top value
+    assert np.allclose(sig, so, rtol=2e-3)                       # clustered community values
