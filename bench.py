@@ -1,0 +1,462 @@
+#!/usr/bin/env python
+"""bench.py -- nodes/sec embedded at d=128 (HOPE, node2vec) on B200 vs the reference's CPU path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload hope|node2vec] [--impl reference]
+
+Default (N=1): BASELINE.json configs[1] -- HOPE d=128, beta=0.01 on the synthetic SBM with
+1,000,000 nodes / ~20M directed edges, one B200.  A "step" is one complete
+learn_embedding-equivalent pass (norm estimate, Katz/SpMM subspace iteration, Rayleigh-Ritz, X) over
+the graph.
+  value : n * K / (sum of the K device times), CSR already resident in HBM, X left on the device;
+          device time = CUDA events inside libgemb200 around the whole solve, max over ranks.
+  e2e   : the same metric through the reference-facing plugin call HOPE.learn_embedding(graph=CSR)
+          with HOST buffers: pinned CSR -> H2D, solve, D2H of the n x d embedding, every step.
+  N > 1 : launched by torchrun, one rank per GPU; weak scaling: n = N * 1,000,000 (rows per GPU fixed),
+          CSR row-sharded, all-gather of the Krylov block per SpMM + b x b all-reduce per Gram (NCCL).
+--workload node2vec: BASELINE.json configs[2] (d=128, p=q=1, 10 walks x 80, context 10, 1 epoch).
+--impl reference: the reference's CPU implementation of the same path on the host cores
+  (HOPE: oracle/hope_oracle.hope_sparse = scipy svds over the matrix-free Katz operator, the only
+  form of hope.py:28-36 that fits in memory beyond ~50k nodes; node2vec: the reference's own SNAP
+  binary from oracle/_ref when present, else oracle/n2v_oracle.c), on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+HOPE_SOLVER = dict(tol=1e-3, max_iters=30, min_iters=2, oversample=16, seed=1234)
+
+
+def read_peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(max(mx)) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------- distributed glue
+def dist_setup(n_gpus):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world == 1:
+        return None, 0, 1, 0
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    assert world == n_gpus, 'WORLD_SIZE %d != --gpus %d' % (world, n_gpus)
+    return dist, rank, world, local
+
+
+def dist_barrier(dist, local):
+    if dist is None:
+        return
+    import torch
+    dist.barrier(device_ids=[local])
+    torch.cuda.synchronize()
+
+
+def dist_max(dist, x, local):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device='cuda:%d' % local)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def dist_sum(dist, x, local):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device='cuda:%d' % local)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ----------------------------------------------------------------------------------- CPU baselines
+def cpu_hope_sample(n_sample, d, beta, tol, seed=42):
+    """The reference path on the host: scipy svds (hope.py:33) over the Katz operator (hope.py:29-31,
+    applied matrix-free).  Returns nodes/s."""
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import hope_oracle as ho
+    from gem_b200 import synth
+    csr = synth.sbm(n=n_sample, block=min(1000, n_sample), seed=seed)
+    A = csr.to_scipy()
+    t = time.perf_counter()
+    X, s, info = ho.hope_sparse(A, d, beta, katz_tol=1e-7, tol=tol)
+    dt = time.perf_counter() - t
+    return n_sample / dt, dt, info
+
+
+def cpu_n2v_sample(n_sample, d, walk_len, num_walks, con_size, threads):
+    """node2vec on the host: the reference's SNAP binary (oracle/_ref/node2vec, all threads) when it is
+    present, else our single-threaded C restatement.  Returns (nodes/s, seconds, kind, cores)."""
+    import tempfile
+    from gem_b200 import synth
+    csr = synth.sbm(n=n_sample, block=min(1000, n_sample), seed=42)
+    exe = os.path.join(REPO, 'oracle/_ref/node2vec')
+    if os.path.exists(exe):
+        with tempfile.TemporaryDirectory() as td:
+            rows = np.repeat(np.arange(csr.n), np.diff(csr.indptr))
+            with open(os.path.join(td, 'g.graph'), 'w') as f:
+                f.write(''.join('%d %d 1.000000\n' % (a, b) for a, b in zip(rows.tolist(), csr.indices.tolist())))
+            env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+            args = [exe, '-i:g.graph', '-o:g.emb', '-d:%d' % d, '-l:%d' % walk_len, '-r:%d' % num_walks,
+                    '-k:%d' % con_size, '-e:1', '-p:1.000000', '-q:1.000000', '-dr', '-w']
+            t = time.perf_counter()
+            subprocess.check_call(args, cwd=td, env=env, stdout=subprocess.DEVNULL)
+            dt = time.perf_counter() - t
+        return n_sample / dt, dt, 'reference', threads
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import n2v_oracle_py as no
+    nids = np.arange(csr.n, dtype=np.int32)
+    t = time.perf_counter()
+    no.node2vec(csr.indptr, csr.indices, None, nids, d, walk_len, num_walks, con_size, 1, seed=1, mode=1)
+    dt = time.perf_counter() - t
+    return n_sample / dt, dt, 'port', 1
+
+
+# ----------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    if args.workload == 'hope':
+        n_s = args.cpu_sample or 50000
+        vals, secs = [], []
+        for _ in range(args.warmup):
+            cpu_hope_sample(n_s, args.d, args.beta, HOPE_SOLVER['tol'])
+        for _ in range(args.steps):
+            v, dt, info = cpu_hope_sample(n_s, args.d, args.beta, HOPE_SOLVER['tol'])
+            vals.append(v); secs.append(dt)
+        value = n_s * len(secs) / sum(secs)
+        kind, used = 'port', 1
+        sample = ('SBM n=%d (same density, seed 42), d=%d, beta=%g, scipy svds(tol=%g, ARPACK) over the matrix-free '
+                  'Katz operator, J=%d Horner terms' % (n_s, args.d, args.beta, HOPE_SOLVER['tol'], info['katz_terms']))
+        cfg = {'workload': 'HOPE d=%d beta=%g, SBM 1M nodes / 20M edges (CPU arm runs a bounded sample)' % (args.d, args.beta)}
+    else:
+        n_s = args.cpu_sample or 4000
+        for _ in range(args.warmup):
+            cpu_n2v_sample(1000, args.d, args.walk_len, args.num_walks, args.con_size, cores)
+        secs = []
+        for _ in range(args.steps):
+            v, dt, kind, used = cpu_n2v_sample(n_s, args.d, args.walk_len, args.num_walks, args.con_size, cores)
+            secs.append(dt)
+        value = n_s * len(secs) / sum(secs)
+        sample = 'SBM n=%d (same density, seed 42), d=%d, r=%d, l=%d, k=%d, 1 epoch' % (
+            n_s, args.d, args.num_walks, args.walk_len, args.con_size)
+        cfg = {'workload': 'node2vec d=%d p=q=1 r=%d l=%d k=%d, SBM 1M nodes / 20M edges (CPU arm runs a bounded sample)' % (
+            args.d, args.num_walks, args.walk_len, args.con_size)}
+    line = {'impl': 'reference', 'metric': 'nodes/sec embedded at d=128', 'value': value, 'unit': 'nodes/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * sum(secs) / len(secs), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': value, 'unit': 'nodes/s', 'cores': used, 'kind': kind, 'sample': sample,
+                             'host_cores': cores},
+            'e2e': {'value': value, 'unit': 'nodes/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- our arm
+def pinned_csr(csr):
+    """Copy of the CSR in pinned host memory with int32 offsets (what gemb_graph_upload reads)."""
+    from gem_b200 import _native
+    from gem_b200.graph import HostCSR
+    ip = _native.pinned_empty(csr.n + 1, np.int32)
+    ip[:] = csr.indptr
+    ix = _native.pinned_empty(max(csr.nnz, 1), np.int32)
+    ix[:csr.nnz] = csr.indices
+    return HostCSR(csr.n, ip, ix[:csr.nnz], None, symmetric=True)
+
+
+def run_hope(args, dist, rank, world, local):
+    from gem_b200 import _native, synth
+    from gem_b200.embedding.hope import HOPE
+    peaks, peak_src = read_peaks()
+    n = args.n * world                                   # weak scaling: rows per GPU fixed
+    t0 = time.perf_counter()
+    csr = synth.sbm(n=n, block=1000, seed=42)            # host, not timed
+    gen_s = time.perf_counter() - t0
+    ctx = _native.Context(local)
+    if world > 1:
+        uid = [_native.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    r0, ip, ix, _ = csr.row_shard(rank, world)
+    g = _native.DeviceGraph(ctx, csr.n, ip, ix, None, row0=r0)
+    solver = dict(HOPE_SOLVER)
+    if args.tol is not None:
+        solver['tol'] = args.tol
+    if args.max_iters is not None:
+        solver['max_iters'] = args.max_iters
+
+    for _ in range(args.warmup):
+        g.hope(args.d, args.beta, want_output=False, **solver)
+    dist_barrier(dist, local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _native.lib().gemb_launch_count()
+    dev_ms, stats = 0.0, None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, st = g.hope(args.d, args.beta, want_output=False, **solver)
+        dev_ms += st['total_ms']
+        stats = st if stats is None else {k: (stats[k] + st[k] if k in ('spmm_ms', 'dense_ms', 'comm_ms', 'spmm_count') else st[k])
+                                          for k in st}
+    dist_barrier(dist, local)
+    wall_s = time.perf_counter() - t0
+    launches = _native.lib().gemb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = dist_max(dist, dev_ms, local)
+    wall_s = dist_max(dist, wall_s, local)
+    value = n * args.steps / (dev_ms * 1e-3)
+
+    # roofline of the dominant kernel (CSR SpMM): algorithmic bytes per launch / mean launch time
+    spmm_ms_per = stats['spmm_ms'] / max(stats['spmm_count'], 1)
+    achieved = stats['spmm_bytes'] / (spmm_ms_per * 1e-3) / 1e9 if spmm_ms_per > 0 else 0.0
+    traffic = None
+    tp = os.path.join(REPO, 'profiles', 'spmm_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+    roofline = {'kernel': 'spmm (CSR x n-by-%d fp32 block)' % stats['block'], 'bound': 'hbm', 'achieved': achieved,
+                'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic,
+                'peak_source': peak_src, 'bytes_per_launch': stats['spmm_bytes'], 'ms_per_launch': spmm_ms_per,
+                'launches_per_step': stats['spmm_count'] / args.steps,
+                'share_of_step': stats['spmm_ms'] / max(dev_ms, 1e-9)}
+
+    # e2e through the plugin class with host buffers (rank-local shard in multi-GPU is not exposed by
+    # the plugin: e2e is measured at N=1 only)
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        hc = pinned_csr(csr)
+        out = _native.pinned_empty((csr.n, args.d), np.float32)
+        HOPE.hyper_params.clear(); HOPE.hyper_params.update({'method_name': 'hope_gsvd'})
+        model = HOPE(d=args.d, beta=args.beta, device=local, **solver)
+        model.learn_embedding(graph=hc, out=out)                      # warm-up
+        t0 = time.perf_counter()
+        ksteps = max(1, min(args.steps, 3))
+        for _ in range(ksteps):
+            X = model.learn_embedding(graph=hc, is_weighted=True, no_python=True, out=out)
+            _ = float(X[0, 0])
+        e2e_s = (time.perf_counter() - t0) / ksteps
+        e2e = {'value': csr.n / e2e_s, 'unit': 'nodes/s', 'ms_per_step': e2e_s * 1e3,
+               'h2d_bytes_per_step': int(hc.indptr.nbytes + hc.indices.nbytes),
+               'd2h_bytes_per_step': int(out.nbytes + 4 * (args.d // 2)), 'steps': ksteps,
+               'call': 'gem_b200.embedding.hope.HOPE(d, beta).learn_embedding(graph=<CSR in pinned host memory>)'}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        n_s = args.cpu_sample or 50000
+        v, dt, info = cpu_hope_sample(n_s, args.d, args.beta, solver['tol'])
+        cpu = {'value': v, 'unit': 'nodes/s', 'cores': 1, 'kind': 'port', 'host_cores': os.cpu_count(),
+               'seconds': dt,
+               'sample': 'SBM n=%d (same density, seed 42), d=%d, beta=%g: scipy svds(tol=%g) over the matrix-free Katz '
+                         'operator (oracle/hope_oracle.hope_sparse), J=%d, %d SpMVs' % (
+                             n_s, args.d, args.beta, solver['tol'], info['katz_terms'], info['spmv'])}
+    g.free()
+    if rank == 0:
+        line = {'metric': 'nodes/sec embedded at d=128', 'value': value, 'unit': 'nodes/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic',
+                'config': {'workload': 'HOPE d=%d beta=%g on SBM n=%d (%d per GPU), nnz=%d directed, 1000-node blocks, '
+                                       'deg 16 in / 4 out, seed 42' % (args.d, args.beta, n, args.n, csr.nnz),
+                           'solver': dict(solver, block=stats['block'], katz_terms=stats['katz_terms'],
+                                          iters=stats['iters'], converged=stats['converged'],
+                                          ritz_change=stats['ritz_change']),
+                           'parallelism': 'row-sharded CSR x%d, all-gather per SpMM' % world if world > 1 else 'single GPU',
+                           'l2_policy': 'inputs larger than L2 (CSR %.0f MB + 5 blocks of %.0f MB vs 126 MB L2)' % (
+                               (csr.nnz * 4 + csr.n * 4) / 1e6, csr.n * stats['block'] * 4 / 1e6 / world)},
+                'wall_ms_per_step': wall_s * 1e3 / args.steps, 'graph_gen_s': gen_s,
+                'phases_ms_per_step': {'spmm': stats['spmm_ms'] / args.steps, 'dense': stats['dense_ms'] / args.steps,
+                                       'comm': stats['comm_ms'] / args.steps},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def run_node2vec(args, dist, rank, world, local):
+    from gem_b200 import _native, synth
+    from gem_b200.embedding.node2vec import node2vec
+    peaks, peak_src = read_peaks()
+    n = args.n * world
+    csr = synth.sbm(n=n, block=1000, seed=42)
+    nids = np.arange(csr.n, dtype=np.int32)
+    ctx = _native.Context(local)
+    if world > 1:
+        uid = [_native.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    g = _native.DeviceGraph(ctx, csr.n, csr.indptr, csr.indices, None)
+    hp = (args.d, args.walk_len, args.num_walks, args.con_size, 1)
+    # warm-up: full-size steps are ~10 s each; warm the kernels on short walks of the same graph
+    for _ in range(args.warmup):
+        g.node2vec(nids, args.d, 8, 1, 4, 1, seed=1, want_output=False)
+    dist_barrier(dist, local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _native.lib().gemb_launch_count()
+    dev_ms, agg = 0.0, None
+    for s in range(args.steps):
+        _, st = g.node2vec(nids, *hp, seed=1 + s, want_output=False)
+        dev_ms += st['total_ms']
+        agg = st if agg is None else {k: agg[k] + st[k] for k in st}
+    dist_barrier(dist, local)
+    launches = _native.lib().gemb_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = dist_max(dist, dev_ms, local)
+    pairs = dist_sum(dist, float(agg['pairs']), local)
+    value = n * args.steps / (dev_ms * 1e-3)
+    sg_bytes = pairs * 14 * 4 * args.d
+    achieved = sg_bytes / world / (agg['sgns_ms'] * 1e-3) / 1e9 if agg['sgns_ms'] > 0 else 0.0
+    roofline = {'kernel': 'sgns (warp per walk, fp32 tables)', 'bound': 'hbm', 'achieved': achieved,
+                'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+                'peak_source': peak_src, 'bytes_per_launch': sg_bytes / world / args.steps,
+                'ms_per_launch': agg['sgns_ms'] / args.steps, 'share_of_step': agg['sgns_ms'] / max(dev_ms, 1e-9),
+                'note': 'algorithmic bytes = 7168 B per (centre, context) pair (SURVEY 8(d)); rows of the walk and the '
+                        'centre row are reused from L1/L2/registers, so achieved may exceed the DRAM peak'}
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        node2vec.hyper_params.clear(); node2vec.hyper_params.update({'method_name': 'node2vec_rw'})
+        model = node2vec(d=args.d, max_iter=1, walk_len=args.walk_len, num_walks=args.num_walks,
+                         con_size=args.con_size, ret_p=1, inout_p=1, device=local)
+        t0 = time.perf_counter()
+        X = model.learn_embedding(graph=(csr, nids))
+        _ = float(X[0, 0])
+        e2e_s = time.perf_counter() - t0
+        e2e = {'value': csr.n / e2e_s, 'unit': 'nodes/s', 'ms_per_step': e2e_s * 1e3,
+               'h2d_bytes_per_step': int(4 * (csr.n + 1) + 4 * csr.nnz + 4 * csr.n * args.num_walks),
+               'd2h_bytes_per_step': int(4 * csr.n * args.d), 'steps': 1,
+               'call': 'gem_b200.embedding.node2vec.node2vec(...).learn_embedding(graph=(CSR, node table))'}
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        n_s = args.cpu_sample or 4000
+        v, dt, kind, used = cpu_n2v_sample(n_s, args.d, args.walk_len, args.num_walks, args.con_size, os.cpu_count() or 1)
+        cpu = {'value': v, 'unit': 'nodes/s', 'cores': used, 'kind': kind, 'host_cores': os.cpu_count(), 'seconds': dt,
+               'sample': 'SBM n=%d (same density, seed 42), d=%d r=%d l=%d k=%d e=1 p=q=1 (%s)' % (
+                   n_s, args.d, args.num_walks, args.walk_len, args.con_size,
+                   'gem/c_exe/node2vec, OMP threads = cores' if kind == 'reference' else 'oracle/n2v_oracle.c, 1 thread')}
+    g.free()
+    if rank == 0:
+        line = {'metric': 'nodes/sec embedded at d=128', 'value': value, 'unit': 'nodes/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'node2vec d=%d p=q=1, %d walks x %d, context %d, 1 epoch, 5 negatives, on SBM n=%d, nnz=%d'
+                                       % (args.d, args.num_walks, args.walk_len, args.con_size, n, csr.nnz),
+                           'parallelism': 'walk-sharded x%d, embedding-delta all-reduce per epoch' % world if world > 1 else 'single GPU',
+                           'l2_policy': 'inputs larger than L2 (two %d MB embedding tables + %d MB walks)' % (
+                               csr.n * args.d * 4 // 10**6, csr.n * args.num_walks * args.walk_len * 4 // 10**6)},
+                'phases_ms_per_step': {k: agg[k] / args.steps for k in ('alias_ms', 'shuffle_ms', 'walk_ms', 'vocab_ms', 'sgns_ms', 'comm_ms')},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='hope', choices=['hope', 'node2vec'])
+    ap.add_argument('--n', type=int, default=1_000_000, help='nodes per GPU')
+    ap.add_argument('--d', type=int, default=128)
+    ap.add_argument('--beta', type=float, default=0.01)
+    ap.add_argument('--tol', type=float, default=None)
+    ap.add_argument('--max-iters', type=int, default=None)
+    ap.add_argument('--walk-len', type=int, default=80)
+    ap.add_argument('--num-walks', type=int, default=10)
+    ap.add_argument('--con-size', type=int, default=10)
+    ap.add_argument('--cpu-sample', type=int, default=None, help='nodes in the CPU baseline sample')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 5 if args.workload == 'hope' else 1
+    if args.impl == 'reference':
+        args.warmup = min(args.warmup, 1)      # each CPU step is a bounded 10-30 s sample
+        run_reference(args)
+        return
+    dist, rank, world, local = dist_setup(args.gpus)
+    try:
+        if args.workload == 'hope':
+            run_hope(args, dist, rank, world, local)
+        else:
+            run_node2vec(args, dist, rank, world, local)
+    finally:
+        if dist is not None:
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

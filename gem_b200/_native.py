@@ -15,7 +15,7 @@ _lib = None
 UNIQUE_ID_BYTES = 128
 
 EXPORTS = [
-    'gemb_version', 'gemb_last_error', 'gemb_device_count', 'gemb_ctx_create', 'gemb_ctx_destroy',
+    'gemb_version', 'gemb_last_error', 'gemb_device_count', 'gemb_launch_count', 'gemb_ctx_create', 'gemb_ctx_destroy',
     'gemb_host_alloc', 'gemb_host_free', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
     'gemb_graph_free', 'gemb_spmm', 'gemb_hope', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
 ]
@@ -64,6 +64,7 @@ def lib():
     L.gemb_version.restype = ctypes.c_int
     L.gemb_last_error.restype = ctypes.c_char_p
     L.gemb_device_count.restype = ctypes.c_int
+    L.gemb_launch_count.restype = ctypes.c_int64
     L.gemb_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
     L.gemb_ctx_destroy.argtypes = [vp]
     L.gemb_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
@@ -119,10 +120,9 @@ def pinned_empty(shape, dtype):
     n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
     owner = _PinnedOwner(max(1, n * dtype.itemsize))
     buf = (ctypes.c_char * owner.nbytes).from_address(owner.ptr)
+    buf._owner = owner          # `buf` is the ultimate .base of every view: the allocation lives as long as any of them
     arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
-    arr = arr.view(PinnedArray)
-    arr._owner = owner
-    return arr
+    return arr.view(PinnedArray)
 
 
 class Context:

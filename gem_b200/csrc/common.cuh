@@ -10,6 +10,7 @@
 namespace gemb {
 
 void set_error(const char *fmt, ...);
+void count_launch(int k = 1);   // every kernel launch of this library is counted (gemb_launch_count)
 
 #define GEMB_CUDA(call)                                                                       \
     do {                                                                                      \
@@ -87,6 +88,9 @@ namespace gemb {
 // global column ids in A.  X0/Y are row shards (ld = b).  All device pointers.
 int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha,
                 const float *X, const float *X0, float *Y);
+// Y = alpha * A * X + gamma * Xself + delta * X0   (Xself / X0: row shards, may be null)
+int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha, const float *X,
+                 float gamma, const float *Xself, float delta, const float *X0, float *Y);
 
 // ---- dense.cu
 // G[b1 x b2] (fp64, row-major, OVERWRITTEN) = P^T Q over n rows (P: n x b1, Q: n x b2, fp32).

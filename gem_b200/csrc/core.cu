@@ -4,10 +4,14 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 
 namespace gemb {
 
 static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch(int k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+long long launches_total() { return g_launches.load(std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -80,6 +84,7 @@ using namespace gemb;
 extern "C" {
 
 int gemb_version(void) { return GEMB_VERSION; }
+int64_t gemb_launch_count(void) { return (int64_t)gemb::launches_total(); }
 const char *gemb_last_error(void) { return g_err; }
 
 int gemb_device_count(void) {

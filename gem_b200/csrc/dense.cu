@@ -101,6 +101,7 @@ int gram_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q
         default: gram_kernel<8><<<grid, block, 0, ctx->stream>>>(n, P, b1, Q, b2, G, tiles_n); break;
     }
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 
@@ -173,6 +174,7 @@ int apply_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *
         default: apply_kernel<8><<<grid, block, 0, ctx->stream>>>(n, Q, b1, M, ldm, b2, Out, ldo); break;
     }
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 
@@ -182,14 +184,21 @@ int apply_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *
 // scale free.  A pivot below PIV_EPS marks the column numerically dependent: its column of Minv is
 // zero (the orthonormalised block then carries a zero column, which stays zero under S).
 #define GEMB_PIV_EPS 1e-5
+// SMEM: the b x b matrix lives in shared memory for the whole factorization (b <= 160).
+template <bool SMEM>
 __global__ void __launch_bounds__(1024)
-chol_inverse_kernel(int b, double *__restrict__ G, float *__restrict__ Minv, int *__restrict__ rank_out) {
+chol_inverse_kernel(int b, double *__restrict__ Gg, float *__restrict__ Minv, int *__restrict__ rank_out) {
     extern __shared__ double sh[];
     double *dscale = sh;           // b : 1/sqrt(G_jj) (0 if G_jj <= 0)
-    double *Linv = sh + b;         // b : 1.0 if column j kept, 0.0 if numerically dependent
+    double *keep = sh + b;         // b : 1.0 if column j kept, 0.0 if numerically dependent
+    double *xdiag = sh + 2 * b;    // b
+    double *G = SMEM ? sh + 3 * b : Gg;
     __shared__ int s_rank;
     const int tid = threadIdx.x, nt = blockDim.x;
-    // scale
+    if (SMEM) {
+        for (int idx = tid; idx < b * b; idx += nt) G[idx] = Gg[idx];
+        __syncthreads();
+    }
     for (int j = tid; j < b; j += nt) {
         const double d = G[(size_t)j * b + j];
         dscale[j] = d > 0.0 ? rsqrt(d) : 0.0;
@@ -201,17 +210,17 @@ chol_inverse_kernel(int b, double *__restrict__ G, float *__restrict__ Minv, int
         G[idx] = G[idx] * dscale[i] * dscale[j];
     }
     __syncthreads();
-    // right-looking Cholesky on the lower triangle: L overwrites G (lower), flags in Linv[j] (0/1)
+    // right-looking Cholesky on the lower triangle: L overwrites G (lower)
     for (int j = 0; j < b; j++) {
         if (tid == 0) {
             const double d = G[(size_t)j * b + j];
             if (d > GEMB_PIV_EPS) {
                 G[(size_t)j * b + j] = sqrt(d);
-                Linv[j] = 1.0;
+                keep[j] = 1.0;
                 s_rank++;
             } else {
                 G[(size_t)j * b + j] = 0.0;
-                Linv[j] = 0.0;
+                keep[j] = 0.0;
             }
         }
         __syncthreads();
@@ -230,23 +239,25 @@ chol_inverse_kernel(int b, double *__restrict__ G, float *__restrict__ Minv, int
         }
         __syncthreads();
     }
-    // R^-1 = D^-1/2 * L^-T.  Column c of L^-1 by forward substitution (thread per column), then
-    // Minv[r][c'] = dscale[r] * (L^-1)[c'][r]   for r <= c'.
-    // Store X = L^-1 into the (now free) strict upper triangle + separate diagonal array.
-    double *xdiag = sh + 2 * b;  // b
-    for (int c = tid; c < b; c += nt) {
-        // solve L x = e_c ; x_i for i >= c ; keep x in upper triangle: U[c][i] := x_i (i > c)
-        const bool okc = Linv[c] != 0.0;
+    // R^-1 = D^-1/2 * L^-T.  Column c of L^-1 by forward substitution (one warp per column, the dot
+    // products split across lanes); x_i (i > c) is kept in the free strict upper triangle G[c][i].
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    for (int c = warp; c < b; c += nwarps) {
+        const bool okc = keep[c] != 0.0;
         const double xc = okc ? 1.0 / G[(size_t)c * b + c] : 0.0;
-        xdiag[c] = xc;
+        if (lane == 0) xdiag[c] = xc;
         for (int i = c + 1; i < b; i++) {
             double s = 0.0;
-            if (okc && Linv[i] != 0.0) {
-                s = G[(size_t)i * b + c] * xc;
-                for (int k = c + 1; k < i; k++) s += G[(size_t)i * b + k] * G[(size_t)c * b + k];
+            if (okc && keep[i] != 0.0) {
+                for (int k = c + 1 + lane; k < i; k += 32) s += G[(size_t)i * b + k] * G[(size_t)c * b + k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                s += G[(size_t)i * b + c] * xc;
                 s = -s / G[(size_t)i * b + i];
             }
-            G[(size_t)c * b + i] = s;  // (L^-1)[i][c]
+            __syncwarp();
+            if (lane == 0) G[(size_t)c * b + i] = s;  // (L^-1)[i][c]
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -261,18 +272,31 @@ chol_inverse_kernel(int b, double *__restrict__ G, float *__restrict__ Minv, int
 }
 
 int chol_inverse_launch(gemb_ctx *ctx, int b, double *G, float *Minv, int *rank_out_dev) {
-    const size_t sh = sizeof(double) * 3 * (size_t)b;
-    chol_inverse_kernel<<<1, 1024, sh, ctx->stream>>>(b, G, Minv, rank_out_dev);
+    const size_t small = sizeof(double) * 3 * (size_t)b;
+    const size_t big = small + sizeof(double) * (size_t)b * b;
+    if (big <= 220 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            GEMB_CUDA(cudaFuncSetAttribute(chol_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            attr_set = true;
+        }
+        chol_inverse_kernel<true><<<1, 1024, big, ctx->stream>>>(b, G, Minv, rank_out_dev);
+    } else {
+        chol_inverse_kernel<false><<<1, 1024, small, ctx->stream>>>(b, G, Minv, rank_out_dev);
+    }
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 
 // ------------------------------------------------------------------------------------ eigh
 // Two-sided cyclic Jacobi with round-robin (circle-method) pair ordering, one CTA, fp64.
 // A is destroyed; w ascending; Z column j <-> w[j].  Zt is b x b scratch.
+// MODE 2: A and Zt in shared memory (b <= 116); MODE 1: A in shared memory (b <= 165); MODE 0: global.
+template <int MODE>
 __global__ void __launch_bounds__(1024)
-eigh_jacobi_kernel(int b, double *__restrict__ A, double *__restrict__ w, double *__restrict__ Z,
-                   double *__restrict__ Zt, int max_sweeps, double rel_tol) {
+eigh_jacobi_kernel(int b, double *__restrict__ Ag, double *__restrict__ w, double *__restrict__ Z,
+                   double *__restrict__ Ztg, int max_sweeps, double rel_tol) {
     extern __shared__ double sh[];
     const int m = (b + 1) & ~1;     // even number of players; index >= b is a dummy
     const int half = m / 2;
@@ -280,9 +304,15 @@ eigh_jacobi_kernel(int b, double *__restrict__ A, double *__restrict__ w, double
     double *sn = sh + half;         // half
     int *pp = (int *)(sh + 2 * half);
     int *qq = pp + half;
+    double *mat = sh + 3 * half + 2;
+    double *A = MODE >= 1 ? mat : Ag;
+    double *Zt = MODE >= 2 ? mat + (size_t)b * b : Ztg;
     __shared__ double s_off, s_diag;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int idx = tid; idx < b * b; idx += nt) Zt[idx] = (idx / b == idx % b) ? 1.0 : 0.0;
+    for (int idx = tid; idx < b * b; idx += nt) {
+        if (MODE >= 1) A[idx] = Ag[idx];
+        Zt[idx] = (idx / b == idx % b) ? 1.0 : 0.0;
+    }
     __syncthreads();
     for (int sweep = 0; sweep < max_sweeps; sweep++) {
         if (tid == 0) { s_off = 0.0; s_diag = 0.0; }
@@ -320,9 +350,9 @@ eigh_jacobi_kernel(int b, double *__restrict__ A, double *__restrict__ w, double
                 pp[tid] = p; qq[tid] = q; cs[tid] = c; sn[tid] = s;
             }
             __syncthreads();
-            // columns: A <- A J, Zt <- Zt J
+            // columns: A <- A J, Zt <- Zt J   (consecutive threads -> different pairs, same row)
             for (int idx = tid; idx < half * b; idx += nt) {
-                const int pi = idx / b, k = idx - pi * b;
+                const int k = idx / half, pi = idx - k * half;
                 const int p = pp[pi], q = qq[pi];
                 if (q < 0) continue;
                 const double c = cs[pi], s = sn[pi];
@@ -335,7 +365,7 @@ eigh_jacobi_kernel(int b, double *__restrict__ A, double *__restrict__ w, double
                 Zt[(size_t)k * b + q] = s * x + c * y;
             }
             __syncthreads();
-            // rows: A <- J^T A
+            // rows: A <- J^T A   (consecutive threads -> consecutive columns)
             for (int idx = tid; idx < half * b; idx += nt) {
                 const int pi = idx / b, k = idx - pi * b;
                 const int p = pp[pi], q = qq[pi];
@@ -350,24 +380,40 @@ eigh_jacobi_kernel(int b, double *__restrict__ A, double *__restrict__ w, double
         }
     }
     __syncthreads();
-    // sort ascending by rank counting, permute eigenvector columns
-    for (int j = tid; j < b; j += nt) {
+    // sort ascending by rank counting, permute eigenvector columns (one warp per eigenvalue)
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    for (int j = warp; j < b; j += nwarps) {
         const double wj = A[(size_t)j * b + j];
         int rank = 0;
-        for (int i = 0; i < b; i++) {
+        for (int i = lane; i < b; i += 32) {
             const double wi = A[(size_t)i * b + i];
             rank += (wi < wj) || (wi == wj && i < j);
         }
-        w[rank] = wj;
-        for (int k = 0; k < b; k++) Z[(size_t)k * b + rank] = Zt[(size_t)k * b + j];
+        for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        if (lane == 0) w[rank] = wj;
+        for (int k = lane; k < b; k += 32) Z[(size_t)k * b + rank] = Zt[(size_t)k * b + j];
     }
 }
 
 int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Zscratch) {
     const int half = ((b + 1) & ~1) / 2;
-    const size_t sh = sizeof(double) * 2 * half + sizeof(int) * 2 * half + 16;
-    eigh_jacobi_kernel<<<1, 1024, sh, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-13);
+    const size_t base = sizeof(double) * (3 * half + 2);
+    const size_t one = sizeof(double) * (size_t)b * b;
+    const size_t cap = 220 * 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GEMB_CUDA(cudaFuncSetAttribute(eigh_jacobi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        GEMB_CUDA(cudaFuncSetAttribute(eigh_jacobi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        attr_set = true;
+    }
+    if (base + 2 * one <= cap)
+        eigh_jacobi_kernel<2><<<1, 1024, base + 2 * one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-13);
+    else if (base + one <= cap)
+        eigh_jacobi_kernel<1><<<1, 1024, base + one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-13);
+    else
+        eigh_jacobi_kernel<0><<<1, 1024, base, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-13);
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 
@@ -397,6 +443,7 @@ int randn_launch(gemb_ctx *ctx, int64_t n, int b, uint64_t seed, uint64_t row_of
     if (tot == 0) return GEMB_OK;
     randn_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(n, b, seed, row_offset, X);
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 
@@ -418,6 +465,7 @@ int sumsq_launch(gemb_ctx *ctx, int64_t count, const float *X, double *out_dev) 
     if ((int64_t)grid * 256 > count) grid = (int)((count + 255) / 256);
     sumsq_kernel<<<grid, 256, 0, ctx->stream>>>(count, X, out_dev);
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 
@@ -433,6 +481,7 @@ int scale_launch(gemb_ctx *ctx, int64_t count, float s, float *X) {
     if ((int64_t)grid * 256 > count) grid = (int)((count + 255) / 256);
     scale_kernel<<<grid, 256, 0, ctx->stream>>>(count, s, X);
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 

@@ -308,11 +308,13 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     GEMB_TRY(c->t_dense.begin(c->stream));
     ritz_maps_kernel<<<(b * k + 255) / 256, 256, 0, c->stream>>>(b, k, W.w, W.Z, W.M1, W.M2, -0.25, 0.25);
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     GEMB_TRY(apply_launch(c, W.rows, U, b, W.M1, k, k, Xd, d));
     GEMB_TRY(apply_launch(c, W.rows, V, b, W.M2, k, k, Xd + k, d));
     float *sig_dev = (float *)W.Minv;  // reuse
     sqrt_top_kernel<<<(k + 127) / 128, 128, 0, c->stream>>>(b, k, W.w, sig_dev);
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     GEMB_TRY(c->t_dense.end(c->stream));
 
     float resid_max = -1.f;
@@ -320,6 +322,7 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         // left vectors P = U Z theta^-1/2 (all b Ritz pairs), right Q = V Z ; check S^T P = Q sigma
         ritz_maps_kernel<<<(b * b + 255) / 256, 256, 0, c->stream>>>(b, b, W.w, W.Z, W.M1, W.M2, -0.5, 0.5);
         GEMB_CUDA(cudaGetLastError());
+    count_launch();
         float *Pm = Wk, *Qs = (Xalloc ? T1 : nullptr);
         float *Qalloc = nullptr;
         if (!Qs) { GEMB_CUDA(cudaMalloc(&Qalloc, blk ? blk : 4)); GEMB_CUDA(cudaMemsetAsync(Qalloc, 0, blk, c->stream)); Qs = Qalloc; }
@@ -336,6 +339,7 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         const int threads = (256 / b) * b > 0 ? (256 / b) * b : b;
         coldiff_sumsq_kernel<<<c->sm_count * 4, threads, 0, c->stream>>>(W.rows, b, STP, Qs, W.scal);
         GEMB_CUDA(cudaGetLastError());
+    count_launch();
         GEMB_TRY(comm_allreduce_f64(W, W.scal, b));
         std::vector<double> rs(b);
         GEMB_CUDA(cudaMemcpyAsync(rs.data(), W.scal, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));

@@ -410,6 +410,7 @@ static int build_alias(gemb_graph *g, const double *weights64, N2VDev &D) {
     const int64_t n = g->n;
     alias_build_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, g->A.indptr, D.w, D.K, D.U, D.scratch);
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 
@@ -433,6 +434,7 @@ static int run_walks(gemb_graph *g, N2VDev &D, const int32_t *nids, int64_t N, i
         walk_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, c->stream>>>(g->A.indptr, g->A.indices, D.K, D.U, D.order,
                                                                          N, walk_len, seed, w_begin, w_end, D.walks);
         GEMB_CUDA(cudaGetLastError());
+    count_launch();
     }
     GEMB_CUDA(cudaStreamSynchronize(c->stream));  // `order` (host) must outlive the async copy
     return GEMB_OK;
@@ -443,6 +445,7 @@ static int launch_sgns(gemb_ctx *c, const SgnsParams &P, int blocks, int threads
     const size_t sh = sizeof(int32_t) * (threads / 32) * P.walk_len;
     sgns_kernel<NV, VEC><<<blocks, threads, sh, c->stream>>>(P);
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 
@@ -574,6 +577,7 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
     if (n_local > 0) {
         vocab_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(D.walks, n_local * walk_len, w_begin * walk_len, D.first_pos, D.cnt);
         GEMB_CUDA(cudaGetLastError());
+    count_launch();
     }
     if (c->nranks > 1) {
         NcclApi *api = nccl_api();
@@ -615,6 +619,7 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
     GEMB_CUDA(cudaMemsetAsync(D.syn_neg, 0, sizeof(float) * tab, c->stream));
     init_pos_kernel<<<(unsigned)((V + 127) / 128), 128, 0, c->stream>>>(V, d, (uint32_t)seed, D.tok2node, D.syn_pos);
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     GEMB_CUDA(cudaMalloc(&D.pairs, sizeof(unsigned long long)));
     GEMB_CUDA(cudaMemsetAsync(D.pairs, 0, sizeof(unsigned long long), c->stream));
     GEMB_CUDA(cudaMalloc(&D.seq_state, sizeof(uint32_t)));
@@ -635,7 +640,14 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
     P.seed = (uint32_t)seed; P.seq_start = (uint64_t)V * d; P.sequential = sequential ? 1 : 0;
     P.seq_state = D.seq_state; P.pair_counter = D.pairs;
     const int threads = 128;
+    // Hogwild: concurrent walks race on embedding rows exactly as SNAP's OpenMP threads do.  Keep the
+    // number of in-flight walks far below the vocabulary size so that lost updates stay as rare as in
+    // the reference (<= 1 walk in flight per 32 tokens), up to 24 warps per SM.
     int blocks = sequential ? 1 : c->sm_count * 6;
+    if (!sequential) {
+        const int64_t max_warps = std::max<int64_t>(1, V / 32);
+        blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (max_warps + 3) / 4));
+    }
     const int threads_used = sequential ? 32 : threads;
     double comm_ms = 0;
     for (int it = 0; it < max_iter; it++) {
@@ -661,6 +673,7 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
             axpy1_kernel<<<gs, 256, 0, c->stream>>>(tabn, D.pos0, D.syn_pos, 1.f);            // + pos0
             if (r != ncclSuccess) { set_error("nccl embedding allreduce: %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
             GEMB_CUDA(cudaGetLastError());
+    count_launch();
             GEMB_TRY(c->t_comm.end(c->stream));
         }
     }

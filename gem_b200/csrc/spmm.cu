@@ -20,11 +20,15 @@ __device__ __forceinline__ void fma4(float4 &a, float v, const float4 &x) {
     a.w = fmaf(v, x.w, a.w);
 }
 
-template <bool HAS_VAL, bool HAS_X0>
+// Y[row] = alpha * (A X)[row] + gamma * Xself[row] + delta * X0[row]
+//   Horner / Katz sweep:      gamma = 0, delta = 1, X0 = the sweep's input block
+//   Chebyshev three-term step: gamma = -2 s c0 / e (current block), delta = -s s' (previous block)
+template <bool HAS_VAL, bool HAS_X0, bool HAS_SELF>
 __global__ void __launch_bounds__(256)
 spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                      const float *__restrict__ vals, int64_t n_rows, int G, int rows_per_cta,
-                     float alpha, const float4 *__restrict__ X, const float4 *__restrict__ X0,
+                     float alpha, float gamma, float delta, const float4 *__restrict__ X,
+                     const float4 *__restrict__ Xself, const float4 *__restrict__ X0,
                      float4 *__restrict__ Y) {
     const int tid = threadIdx.x;
     const int lr = tid / G;
@@ -62,18 +66,30 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
         fma4(acc, v0, x0);
     }
     float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+    if (HAS_SELF) {
+        const float4 z = __ldg(Xself + row * G + c);
+        r.x = fmaf(gamma, z.x, r.x);
+        r.y = fmaf(gamma, z.y, r.y);
+        r.z = fmaf(gamma, z.z, r.z);
+        r.w = fmaf(gamma, z.w, r.w);
+    }
     if (HAS_X0) {
         const float4 z = __ldg(X0 + row * G + c);
-        r.x += z.x;
-        r.y += z.y;
-        r.z += z.z;
-        r.w += z.w;
+        r.x = fmaf(delta, z.x, r.x);
+        r.y = fmaf(delta, z.y, r.y);
+        r.z = fmaf(delta, z.z, r.z);
+        r.w = fmaf(delta, z.w, r.w);
     }
     Y[row * G + c] = r;
 }
 
 int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha,
                 const float *X, const float *X0, float *Y) {
+    return spmm3_launch(ctx, A, n_rows, b, alpha, X, 0.f, nullptr, 1.f, X0, Y);
+}
+
+int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha, const float *X,
+                 float gamma, const float *Xself, float delta, const float *X0, float *Y) {
     GEMB_ARG(b > 0 && b % 4 == 0 && b <= 1024, "block width must be a multiple of 4, <= 1024");
     if (n_rows == 0) return GEMB_OK;
     const int G = b / 4;
@@ -81,18 +97,25 @@ int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, flo
     const int64_t grid = (n_rows + rows_per_cta - 1) / rows_per_cta;
     GEMB_ARG(grid < (int64_t)2147483647, "grid too large");
     dim3 g((unsigned)grid), t(256);
-    const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0;
+    const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0, *XS4 = (const float4 *)Xself;
     float4 *Y4 = (float4 *)Y;
-#define LAUNCH(V, Z)                                                                              \
-    spmm_rowgroup_kernel<V, Z><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G,  \
-                                                         rows_per_cta, alpha, X4, X04, Y4)
-    if (A.data) {
-        if (X0) LAUNCH(true, true); else LAUNCH(true, false);
-    } else {
-        if (X0) LAUNCH(false, true); else LAUNCH(false, false);
+#define LAUNCH(V, Z, S)                                                                              \
+    spmm_rowgroup_kernel<V, Z, S><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G,  \
+                                                            rows_per_cta, alpha, gamma, delta, X4, XS4, X04, Y4)
+    const int sel = (A.data ? 4 : 0) | (X0 ? 2 : 0) | (Xself ? 1 : 0);
+    switch (sel) {
+        case 0: LAUNCH(false, false, false); break;
+        case 1: LAUNCH(false, false, true); break;
+        case 2: LAUNCH(false, true, false); break;
+        case 3: LAUNCH(false, true, true); break;
+        case 4: LAUNCH(true, false, false); break;
+        case 5: LAUNCH(true, false, true); break;
+        case 6: LAUNCH(true, true, false); break;
+        default: LAUNCH(true, true, true); break;
     }
 #undef LAUNCH
     GEMB_CUDA(cudaGetLastError());
+    count_launch();
     return GEMB_OK;
 }
 

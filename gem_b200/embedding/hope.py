@@ -48,7 +48,7 @@ class HOPE(StaticGraphEmbedding):
             return _graph.from_networkx(graph)
         return _graph.from_scipy(graph)
 
-    def learn_embedding(self, graph=None, is_weighted=False, no_python=False, **ignored):
+    def learn_embedding(self, graph=None, is_weighted=False, no_python=False, out=None, **ignored):
         if graph is None or (hasattr(graph, '__len__') and len(graph) == 0) or \
                 (hasattr(graph, 'shape') and graph.shape[0] == 0):
             raise ValueError('graph needed')
@@ -63,7 +63,7 @@ class HOPE(StaticGraphEmbedding):
                 g = _native.DeviceGraph(ctx, csr.n, csr.indptr, csr.indices, csr.data_f32(),
                                         t.indptr, t.indices, t.data_f32())
             try:
-                X, sigma, st = g.hope(int(self._d), float(self._beta), **opts)
+                X, sigma, st = g.hope(int(self._d), float(self._beta), out=out, **opts)
             finally:
                 g.free()
         finally:

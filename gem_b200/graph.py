@@ -12,12 +12,16 @@ class HostCSR:
     """n x n CSR with int64 indptr, int32 column ids sorted within each row, optional fp64 weights
     (None = all 1.0).  `nodes` = the node label of each row (HOPE: list(graph.nodes) order)."""
 
-    def __init__(self, n, indptr, indices, data=None, nodes=None):
+    def __init__(self, n, indptr, indices, data=None, nodes=None, symmetric=None):
         self.n = int(n)
-        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indptr = np.asarray(indptr)
+        # int32 offsets are kept as they are (what gemb_graph_upload takes; may live in pinned memory)
+        self.indptr = indptr if (indptr.dtype == np.int32 and indptr.flags.c_contiguous) \
+            else np.ascontiguousarray(indptr, dtype=np.int64)
         self.indices = np.ascontiguousarray(indices, dtype=np.int32)
         self.data = None if data is None else np.ascontiguousarray(data, dtype=np.float64)
         self.nodes = nodes
+        self.symmetric = symmetric      # None = unknown (is_symmetric() computes it)
         assert self.indptr.shape[0] == self.n + 1
 
     @property
@@ -28,16 +32,18 @@ class HostCSR:
         return None if self.data is None else self.data.astype(np.float32)
 
     def transpose(self):
-        rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(self.indptr))
+        rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(self.indptr).astype(np.int64))
         return from_edges(self.n, self.indices, rows, self.data, nodes=self.nodes)
 
     def is_symmetric(self):
+        if self.symmetric is not None:
+            return bool(self.symmetric)
         t = self.transpose()
-        if not (np.array_equal(t.indptr, self.indptr) and np.array_equal(t.indices, self.indices)):
-            return False
-        if self.data is None:
-            return True
-        return bool(np.array_equal(t.data, self.data))
+        sym = bool(np.array_equal(t.indptr, self.indptr) and np.array_equal(t.indices, self.indices))
+        if sym and self.data is not None:
+            sym = bool(np.array_equal(t.data, self.data))
+        self.symmetric = sym
+        return sym
 
     def row_shard(self, rank, nranks):
         """Rows [rank*ceil(n/P), ...) with shard-local offsets (the layout gemb_graph_upload wants)."""

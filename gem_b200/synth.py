@@ -20,7 +20,7 @@ def _csr_from_pairs(n, u, v):
     dst = (key - src * n).astype(np.int32)
     indptr = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.bincount(src, minlength=n), out=indptr[1:])
-    return HostCSR(n, indptr, dst, None)
+    return HostCSR(n, indptr, dst, None, symmetric=True)
 
 
 def sbm(n=1_000_000, block=1000, deg_in=16.0, deg_out=4.0, seed=42):

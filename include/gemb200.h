@@ -44,6 +44,7 @@ typedef struct gemb_graph gemb_graph; /* a CSR row shard (and its transpose) res
 int gemb_version(void);
 const char *gemb_last_error(void);
 int gemb_device_count(void); /* number of CUDA devices, 0 if none / no driver */
+int64_t gemb_launch_count(void); /* kernels this library has launched in this process so far */
 
 int gemb_ctx_create(int device, gemb_ctx **out);
 int gemb_ctx_destroy(gemb_ctx *ctx);
