@@ -17,7 +17,7 @@ UNIQUE_ID_BYTES = 128
 EXPORTS = [
     'gemb_version', 'gemb_last_error', 'gemb_device_count', 'gemb_launch_count', 'gemb_ctx_create', 'gemb_ctx_destroy',
     'gemb_host_alloc', 'gemb_host_free', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
-    'gemb_graph_free', 'gemb_spmm', 'gemb_hope', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
+    'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_hope', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
 ]
 
 
@@ -25,12 +25,14 @@ class HopeOpts(ctypes.Structure):
     _fields_ = [('struct_size', ctypes.c_uint32), ('oversample', ctypes.c_int32),
                 ('max_iters', ctypes.c_int32), ('min_iters', ctypes.c_int32), ('tol', ctypes.c_float),
                 ('katz_terms', ctypes.c_int32), ('katz_tol', ctypes.c_float), ('seed', ctypes.c_uint64),
-                ('compute_residual', ctypes.c_int32), ('verbose', ctypes.c_int32)]
+                ('compute_residual', ctypes.c_int32), ('verbose', ctypes.c_int32),
+                ('algorithm', ctypes.c_int32), ('cheb_degree', ctypes.c_int32)]
 
 
 class HopeStats(ctypes.Structure):
     _fields_ = [('struct_size', ctypes.c_uint32), ('iters', ctypes.c_int32), ('katz_terms', ctypes.c_int32),
-                ('block', ctypes.c_int32), ('converged', ctypes.c_int32), ('spmm_count', ctypes.c_int64),
+                ('block', ctypes.c_int32), ('converged', ctypes.c_int32), ('algorithm', ctypes.c_int32),
+                ('spmm_count', ctypes.c_int64),
                 ('spmm_ms', ctypes.c_double), ('spmm_bytes', ctypes.c_double), ('dense_ms', ctypes.c_double),
                 ('comm_ms', ctypes.c_double), ('total_ms', ctypes.c_double), ('h2d_ms', ctypes.c_double),
                 ('d2h_ms', ctypes.c_double), ('norm2_A', ctypes.c_float), ('ritz_change', ctypes.c_float),
@@ -74,6 +76,7 @@ def lib():
     L.gemb_graph_upload.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]
     L.gemb_graph_free.argtypes = [vp]
     L.gemb_spmm.argtypes = [vp, ctypes.c_int, ctypes.c_int, f32, vp, vp, vp]
+    L.gemb_gram.argtypes = [vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
     L.gemb_hope.argtypes = [vp, ctypes.c_int, f32, ctypes.POINTER(HopeOpts), vp, vp, ctypes.POINTER(HopeStats)]
     L.gemb_n2v_alias.argtypes = [vp, vp, vp, vp]
     L.gemb_n2v_walks.argtypes = [vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, f64, f64, i32, i64, i64, vp,
@@ -139,6 +142,15 @@ class Context:
         check(lib().gemb_comm_init(self._h, int(rank), int(nranks), buf))
         self.rank, self.nranks = int(rank), int(nranks)
 
+    def gram(self, P, Q=None, tensor_cores=True):
+        """G = P^T Q (fp64) through the device kernels (test hook)."""
+        P = np.ascontiguousarray(P, dtype=np.float32)
+        Qc = None if Q is None else np.ascontiguousarray(Q, dtype=np.float32)
+        b1, b2 = P.shape[1], (P.shape[1] if Qc is None else Qc.shape[1])
+        G = np.empty((b1, b2), dtype=np.float64)
+        check(lib().gemb_gram(self._h, P.shape[0], _ptr(P), b1, _ptr(Qc), b2, int(bool(tensor_cores)), _ptr(G)))
+        return G
+
     def close(self):
         if self._h:
             lib().gemb_ctx_destroy(self._h)
@@ -193,7 +205,8 @@ class DeviceGraph:
                      max_iters=int(opts.get('max_iters', 0)), min_iters=int(opts.get('min_iters', 0)),
                      tol=float(opts.get('tol', 0.0)), katz_terms=int(opts.get('katz_terms', 0)),
                      katz_tol=float(opts.get('katz_tol', 0.0)), seed=int(opts.get('seed', 0)),
-                     compute_residual=int(opts.get('compute_residual', 0)), verbose=int(opts.get('verbose', 0)))
+                     compute_residual=int(opts.get('compute_residual', 0)), verbose=int(opts.get('verbose', 0)),
+                     algorithm=int(opts.get('algorithm', 0)), cheb_degree=int(opts.get('cheb_degree', 0)))
         st = HopeStats(struct_size=ctypes.sizeof(HopeStats))
         X = sig = None
         if want_output:

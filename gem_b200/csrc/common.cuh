@@ -101,7 +101,12 @@ int apply_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *
 // Small b x b factorizations, single CTA, fp64 (device pointers):
 //  chol_inverse: G (b x b, SPD up to rank deficiency) -> Minv fp32 (b x b) with G = R^T R, Minv = R^-1
 //  (columns whose pivot falls below eps*max are zeroed: Q*Minv then has zero columns there).
-int chol_inverse_launch(gemb_ctx *ctx, int b, double *G, float *Minv, int *rank_out_dev);
+int chol_inverse_launch(gemb_ctx *ctx, int b, double *G, float *Minv, int *rank_out_dev, double *Minv64 = nullptr);
+//  C (fp64) and/or C32 (fp32) = op(A) * B for b x b fp64 matrices (one CTA)
+int small_gemm_launch(gemb_ctx *ctx, int b, const double *A, int transA, const double *B, double *C, float *C32);
+// CUDA-core Gram (gram_launch prefers the tcgen05 kernel in gram_tc.cu when the shape fits)
+int gram_fp32_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G);
+int gram_tc_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G);
 //  eigh: G -> eigenvalues w ascending (b), eigenvectors Z (b x b, column j <-> w[j]); G destroyed.
 int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Zscratch /* b x b */);
 int randn_launch(gemb_ctx *ctx, int64_t n, int b, uint64_t seed, uint64_t row_offset, float *X);

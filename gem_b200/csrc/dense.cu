@@ -6,6 +6,8 @@
 // These replace numpy.linalg.qr / svd inside scipy's svds (hope.py:33 -> _svds.py:508-533).
 // fp32 data, fp32 FMA inside a CTA's partial sums, fp64 across CTAs and in the b x b algebra.
 #include "common.cuh"
+#include <stdlib.h>
+#include <algorithm>
 
 namespace gemb {
 
@@ -82,7 +84,28 @@ static int pick_tm(int b) {
     return best;
 }
 
+int gram_tc_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G);
+
+static int gram_mode() {   // GEMB_GRAM=fp32 forces the CUDA-core kernel (A/B testing); default = tcgen05
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("GEMB_GRAM");
+        mode = (e && (e[0] == 'f' || e[0] == '0')) ? 0 : 1;
+    }
+    return mode;
+}
+
+int gram_fp32_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G);
+
 int gram_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G) {
+    if (gram_mode() == 1 && n >= 4096) {
+        const int s = gram_tc_launch(ctx, n, P, b1, Q, b2, G);
+        if (s != GEMB_ERR_UNSUPPORTED) return s;
+    }
+    return gram_fp32_launch(ctx, n, P, b1, Q, b2, G);
+}
+
+int gram_fp32_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G) {
     GEMB_CUDA(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)b1 * b2, ctx->stream));
     if (n == 0) return GEMB_OK;
     const int bmax = b1 > b2 ? b1 : b2;
@@ -187,7 +210,8 @@ int apply_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *
 // SMEM: the b x b matrix lives in shared memory for the whole factorization (b <= 160).
 template <bool SMEM>
 __global__ void __launch_bounds__(1024)
-chol_inverse_kernel(int b, double *__restrict__ Gg, float *__restrict__ Minv, int *__restrict__ rank_out) {
+chol_inverse_kernel(int b, double *__restrict__ Gg, float *__restrict__ Minv, double *__restrict__ Minv64,
+                    int *__restrict__ rank_out) {
     extern __shared__ double sh[];
     double *dscale = sh;           // b : 1/sqrt(G_jj) (0 if G_jj <= 0)
     double *keep = sh + b;         // b : 1.0 if column j kept, 0.0 if numerically dependent
@@ -267,11 +291,12 @@ chol_inverse_kernel(int b, double *__restrict__ Gg, float *__restrict__ Minv, in
         if (r == c) v = xdiag[r] * dscale[r];
         else if (r < c) v = G[(size_t)r * b + c] * dscale[r];
         Minv[idx] = (float)v;
+        if (Minv64) Minv64[idx] = v;
     }
     if (tid == 0 && rank_out) *rank_out = s_rank;
 }
 
-int chol_inverse_launch(gemb_ctx *ctx, int b, double *G, float *Minv, int *rank_out_dev) {
+int chol_inverse_launch(gemb_ctx *ctx, int b, double *G, float *Minv, int *rank_out_dev, double *Minv64) {
     const size_t small = sizeof(double) * 3 * (size_t)b;
     const size_t big = small + sizeof(double) * (size_t)b * b;
     if (big <= 220 * 1024) {
@@ -280,9 +305,9 @@ int chol_inverse_launch(gemb_ctx *ctx, int b, double *G, float *Minv, int *rank_
             GEMB_CUDA(cudaFuncSetAttribute(chol_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             attr_set = true;
         }
-        chol_inverse_kernel<true><<<1, 1024, big, ctx->stream>>>(b, G, Minv, rank_out_dev);
+        chol_inverse_kernel<true><<<1, 1024, big, ctx->stream>>>(b, G, Minv, Minv64, rank_out_dev);
     } else {
-        chol_inverse_kernel<false><<<1, 1024, small, ctx->stream>>>(b, G, Minv, rank_out_dev);
+        chol_inverse_kernel<false><<<1, 1024, small, ctx->stream>>>(b, G, Minv, Minv64, rank_out_dev);
     }
     GEMB_CUDA(cudaGetLastError());
     count_launch();
@@ -417,6 +442,28 @@ int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Z
     return GEMB_OK;
 }
 
+// ------------------------------------------------------------------------------------ small b x b products
+// C = op(A) * B, all b x b fp64 row-major (one CTA; used for the Ritz rotation of Gram matrices)
+__global__ void __launch_bounds__(1024)
+small_gemm_kernel(int b, const double *__restrict__ A, int transA, const double *__restrict__ B,
+                  double *__restrict__ C, float *__restrict__ C32) {
+    for (int idx = threadIdx.x; idx < b * b; idx += blockDim.x) {
+        const int i = idx / b, j = idx - i * b;
+        double acc = 0.0;
+        if (transA) for (int k = 0; k < b; k++) acc += A[(size_t)k * b + i] * B[(size_t)k * b + j];
+        else for (int k = 0; k < b; k++) acc += A[(size_t)i * b + k] * B[(size_t)k * b + j];
+        if (C) C[idx] = acc;
+        if (C32) C32[idx] = (float)acc;
+    }
+}
+
+int small_gemm_launch(gemb_ctx *ctx, int b, const double *A, int transA, const double *B, double *C, float *C32) {
+    small_gemm_kernel<<<1, 1024, 0, ctx->stream>>>(b, A, transA, B, C, C32);
+    GEMB_CUDA(cudaGetLastError());
+    count_launch();
+    return GEMB_OK;
+}
+
 // ------------------------------------------------------------------------------------ misc
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -486,3 +533,29 @@ int scale_launch(gemb_ctx *ctx, int64_t count, float s, float *X) {
 }
 
 }  // namespace gemb
+
+extern "C" int gemb_gram(gemb_ctx *c, int64_t n, const float *P, int b1, const float *Q, int b2,
+                         int use_tensor_cores, double *G_out) {
+    using namespace gemb;
+    GEMB_ARG(c && P && G_out && n >= 0 && b1 > 0 && b2 > 0, "ctx/P/G/n/b");
+    GEMB_CUDA(cudaSetDevice(c->device));
+    float *dP = nullptr, *dQ = nullptr;
+    double *dG = nullptr;
+    GEMB_CUDA(cudaMalloc(&dP, sizeof(float) * (size_t)std::max<int64_t>(n, 1) * b1));
+    GEMB_CUDA(cudaMemcpyAsync(dP, P, sizeof(float) * (size_t)n * b1, cudaMemcpyHostToDevice, c->stream));
+    if (Q) {
+        GEMB_CUDA(cudaMalloc(&dQ, sizeof(float) * (size_t)std::max<int64_t>(n, 1) * b2));
+        GEMB_CUDA(cudaMemcpyAsync(dQ, Q, sizeof(float) * (size_t)n * b2, cudaMemcpyHostToDevice, c->stream));
+    }
+    GEMB_CUDA(cudaMalloc(&dG, sizeof(double) * (size_t)b1 * b2));
+    int s = use_tensor_cores ? gram_tc_launch(c, n, dP, b1, Q ? dQ : dP, b2, dG)
+                             : gram_fp32_launch(c, n, dP, b1, Q ? dQ : dP, b2, dG);
+    if (s == GEMB_ERR_UNSUPPORTED) set_error("gemb_gram: shape (n=%lld, b1=%d, b2=%d) not supported by the tcgen05 kernel", (long long)n, b1, b2);
+    if (s == GEMB_OK) {
+        cudaError_t e = cudaMemcpyAsync(G_out, dG, sizeof(double) * (size_t)b1 * b2, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { set_error("gemb_gram: %s", cudaGetErrorString(e)); s = GEMB_ERR_CUDA; }
+    }
+    cudaFree(dP); cudaFree(dQ); cudaFree(dG);
+    return s;
+}

@@ -1,17 +1,33 @@
 // gem_b200/csrc/hope.cu -- HOPE: top-k SVD of the Katz proximity S = (I - beta A)^-1 beta A without
 // ever forming S (replaces hope.py:29-36 and scipy svds, _svds.py:432-535).
 //
-// Algorithm (block subspace iteration with Rayleigh-Ritz on S^T S, the block form of what ARPACK
-// does for svds: SURVEY Appendix B):
+// Two solvers behind gemb_hope():
+//
+//  GENERAL (any A; algorithm = 1): block subspace iteration with Rayleigh-Ritz on S^T S, the block
+//  form of what ARPACK does for svds.  S.x and S^T.x are Katz/Horner sweeps of
+//  the CSR SpMM:
 //     V <- orth(randn(n, b))                                   b = k + oversample
 //     repeat
-//         U  = S V                       J Horner sweeps of CSR SpMM      (katz)
-//         T  = U^T U  = V^T S^T S V ;  (theta, Z) = eigh(T)    Ritz values theta = sigma^2
+//         U  = S V                       J SpMM sweeps
+//         T  = U^T U ;  (theta, Z) = eigh(T)                   Ritz values theta = sigma^2
 //         stop if the top-k theta moved by <= tol * theta_max  (or max_iters)
-//         U <- U R^-1   (CholeskyQR from T)
-//         W  = S^T U ;  V <- orth(W)     (CholeskyQR2)
-//     sigma_j = sqrt(theta_j) ascending over the top k;  X = [ U Z_k theta^-1/4 | V Z_k theta^1/4 ]
-//       (U = S V un-normalised:  U Z_k / sigma = left vectors, V Z_k = right vectors)
+//         U <- U Z Theta^-1/2 (orthonormal Ritz vectors);  W = S^T U ;  V <- CholQR2(W)
+//     sigma = sqrt(theta) ascending over the top k;  X = [ U Z_k theta^-1/4 | V Z_k theta^1/4 ]
+//
+//  SYMMETRIC (A = A^T, which gemb_graph_upload knows; algorithm = 2, the default for symmetric
+//  shards): S = f(A) with f(l) = beta l / (1 - beta l) shares A's eigenvectors, so the singular
+//  triplets of S are (|f(l_i)|, sign(f(l_i)) v_i, v_i).  The invariant subspace is found by
+//  Chebyshev-filtered subspace iteration on A itself -- one SpMM per polynomial degree instead of J
+//  per operator application -- with the damped interval set each round to {l : |f(l)| < tau}, tau the
+//  smallest |f| among the block's Ritz values:
+//     V <- CholQR2(randn)
+//     repeat
+//         W = A V;  T = V^T W;  (l, Z) = eigh(T)               Rayleigh-Ritz on A
+//         theta_i = f(l_i)^2, ranked;  stop on the same test as above
+//         F = W (first 3 rounds: power step) or p_m(A) V       scaled three-term recurrence, fused SpMM epilogue
+//         V <- orth(F) by CholeskyQR2 on the Ritz-rotated block F Z (well conditioned for any filter gain)
+//     X = [ V Z_k sign(f) sqrt(sigma) | V Z_k sqrt(sigma) ]
+//
 // Multi-GPU: rows are sharded; each SpMM is preceded by an all-gather of the block's row shards
 // and each Gram matrix is all-reduced (b x b fp64).
 #include "common.cuh"
@@ -19,6 +35,7 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <numeric>
 
 namespace gemb {
 
@@ -39,6 +56,16 @@ struct HopeWork {
         cudaFree(full); cudaFree(G); cudaFree(G2); cudaFree(w); cudaFree(Z); cudaFree(Zs); cudaFree(scal);
         cudaFree(Minv); cudaFree(M1); cudaFree(M2); cudaFree(rank_dev);
     }
+};
+
+struct HopeResult {
+    int iters = 0, converged = 0, katz_terms = 0, algorithm = 0;
+    double change = 0.0;
+    float resid_max = -1.f;
+    float *Xd = nullptr;       // device n_local x d (points into a work buffer or Xalloc)
+    float *Xalloc = nullptr;   // owned
+    float *sig_dev = nullptr;  // k floats
+    double sigma_max = 0.0;
 };
 
 static int comm_allgather(HopeWork &W, const float *shard_src, int width) {
@@ -63,19 +90,25 @@ static int comm_allreduce_f64(HopeWork &W, double *buf, size_t count) {
     return GEMB_OK;
 }
 
-// Y(shard) = X0 + alpha * op(A) * X(shard) ; X is all-gathered first when sharded
-static int dist_spmm(HopeWork &W, bool transpose, int width, float alpha, const float *Xshard,
-                     const float *X0, float *Y, bool timed) {
+// Y(shard) = alpha * op(A) * X + gamma * X(shard) + delta * X0(shard); X is all-gathered first when sharded
+static int dist_spmm3(HopeWork &W, bool transpose, int width, float alpha, const float *Xshard, float gamma,
+                      bool use_self, float delta, const float *X0, float *Y, bool timed) {
     const float *Xfull = Xshard;
     if (W.c->nranks > 1) {
         GEMB_TRY(comm_allgather(W, Xshard, width));
         Xfull = W.full;
     }
     if (timed) GEMB_TRY(W.c->t_spmm.begin(W.c->stream));
-    GEMB_TRY(spmm_launch(W.c, transpose ? W.g->AT : W.g->A, W.rows, width, alpha, Xfull, X0, Y));
+    GEMB_TRY(spmm3_launch(W.c, transpose ? W.g->AT : W.g->A, W.rows, width, alpha, Xfull, gamma,
+                          use_self ? Xshard : nullptr, delta, X0, Y));
     if (timed) { GEMB_TRY(W.c->t_spmm.end(W.c->stream)); W.spmm_wide++; }
     W.spmm_all++;
     return GEMB_OK;
+}
+
+static int dist_spmm(HopeWork &W, bool transpose, int width, float alpha, const float *Xshard,
+                     const float *X0, float *Y, bool timed) {
+    return dist_spmm3(W, transpose, width, alpha, Xshard, 0.f, false, 1.f, X0, Y, timed);
 }
 
 // out = sum_{j=1..J} (beta op(A))^j in   (Horner: W_m = in + beta op(A) W_{m-1}); t1,t2 scratch
@@ -111,9 +144,19 @@ static int cholqr_pass(HopeWork &W, double *G, const float *src, float *dst) {
     return GEMB_OK;
 }
 
+// dst = orth(src) by CholeskyQR2; tmp is scratch; src, tmp, dst pairwise distinct
+static int cholqr2(HopeWork &W, const float *src, float *tmp, float *dst) {
+    GEMB_TRY(gram_full(W, src, src, W.G));
+    GEMB_TRY(cholqr_pass(W, W.G, src, tmp));
+    GEMB_TRY(gram_full(W, tmp, tmp, W.G));
+    GEMB_TRY(cholqr_pass(W, W.G, tmp, dst));
+    return GEMB_OK;
+}
+
 // M1[i][j] = Z[i][b-k+j] * theta_j^(p1),  M2 likewise with p2   (theta ascending, top k)
 __global__ void ritz_maps_kernel(int b, int k, const double *__restrict__ w, const double *__restrict__ Z,
-                                 float *__restrict__ M1, float *__restrict__ M2, double p1, double p2) {
+                                 float *__restrict__ M1, float *__restrict__ M2, double p1, double p2,
+                                 double rel_floor = 1e-28) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= b * k) return;
     const int i = idx / k, j = idx - i * k;
@@ -121,7 +164,7 @@ __global__ void ritz_maps_kernel(int b, int k, const double *__restrict__ w, con
     const double th = w[b - k + j];
     const double z = Z[(size_t)i * b + (b - k + j)];
     double a = 0.0, c = 0.0;
-    if (th > 1e-28 * wmax && th > 0.0) { a = z * pow(th, p1); c = z * pow(th, p2); }
+    if (th > rel_floor * wmax && th > 0.0) { a = z * pow(th, p1); c = z * pow(th, p2); }
     M1[idx] = (float)a;
     M2[idx] = (float)c;
 }
@@ -144,6 +187,362 @@ __global__ void coldiff_sumsq_kernel(int64_t n, int b, const float *__restrict__
     atomicAdd(out + j, acc);
 }
 
+// T <- (T + T^T) / 2
+__global__ void symmetrize_kernel(int b, double *__restrict__ T) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= b * b) return;
+    const int i = idx / b, j = idx - i * b;
+    if (i < j) {
+        const double v = 0.5 * (T[(size_t)i * b + j] + T[(size_t)j * b + i]);
+        T[(size_t)i * b + j] = v;
+        T[(size_t)j * b + i] = v;
+    }
+}
+
+// Y = a * P + c * Q
+__global__ void axpby_kernel(int64_t count, float a, const float4 *__restrict__ P, float c,
+                             const float4 *__restrict__ Q, float4 *__restrict__ Y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 p = P[i], q = Q[i];
+        Y[i] = make_float4(a * p.x + c * q.x, a * p.y + c * q.y, a * p.z + c * q.z, a * p.w + c * q.w);
+    }
+}
+
+static int axpby_launch(HopeWork &W, float a, const float *P, float c, const float *Q, float *Y) {
+    const int64_t count = W.rows * (int64_t)W.b / 4;
+    if (count == 0) return GEMB_OK;
+    int grid = W.c->sm_count * 8;
+    if ((int64_t)grid * 256 > count) grid = (int)((count + 255) / 256);
+    axpby_kernel<<<grid, 256, 0, W.c->stream>>>(count, a, (const float4 *)P, c, (const float4 *)Q, (float4 *)Y);
+    GEMB_CUDA(cudaGetLastError());
+    count_launch();
+    return GEMB_OK;
+}
+
+// ||A||_2 by power iteration on A^T A with a 4-column block
+static int estimate_norm2(HopeWork &W, uint64_t seed, float *x, float *y, float *z, double *out) {
+    gemb_ctx *c = W.c;
+    gemb_graph *g = W.g;
+    const int pw = 4;
+    GEMB_TRY(randn_launch(c, W.rows, pw, seed ^ 0x5bd1e995u, (uint64_t)g->row0, x));
+    double est = 0.0, prev = -1.0;
+    for (int it = 0; it < 16; it++) {
+        double h[2];
+        GEMB_TRY(sumsq_launch(c, W.rows * pw, x, W.scal));
+        GEMB_TRY(dist_spmm(W, false, pw, 1.f, x, nullptr, y, false));
+        GEMB_TRY(dist_spmm(W, true, pw, 1.f, y, nullptr, z, false));
+        GEMB_TRY(sumsq_launch(c, W.rows * pw, z, W.scal + 1));
+        GEMB_TRY(comm_allreduce_f64(W, W.scal, 2));
+        GEMB_CUDA(cudaMemcpyAsync(h, W.scal, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        if (!(h[0] > 0.0) || !(h[1] > 0.0)) { est = 0.0; break; }  // A^T A x = 0 (empty graph)
+        est = sqrt(sqrt(h[1] / h[0]));   // ||A^T A x|| / ||x|| -> sigma_max^2
+        GEMB_TRY(scale_launch(c, W.rows * pw, (float)(1.0 / sqrt(h[1])), z));
+        std::swap(x, z);
+        if (prev > 0 && fabs(est - prev) <= 1e-3 * est && it >= 3) break;
+        prev = est;
+    }
+    *out = est;
+    return GEMB_OK;
+}
+
+struct Opts {
+    int oversample = 16, max_iters = 30, min_iters = 2, katz_terms = 0, compute_residual = 0, verbose = 0;
+    int algorithm = 0, cheb_degree = 8;
+    float tol = 1e-6f, katz_tol = 1e-7f;
+    uint64_t seed = 1234;
+};
+
+static int katz_terms_for(double beta, double nrm, double katz_tol) {
+    const double x1 = beta * nrm * 1.02;
+    if (x1 <= 1e-30) return 1;
+    int J = (int)ceil(log(katz_tol) / log(x1));
+    return std::max(1, std::min(J, 4096));
+}
+
+// max over `cols` of || S^T P_j - Qs_j || / smax ;  scr0..2 are scratch blocks
+static int residual_check(HopeWork &W, float beta, int J, const float *P, const float *Qs, float *scr0, float *scr1,
+                          float *scr2, const std::vector<int> &cols, double smax, float *out) {
+    gemb_ctx *c = W.c;
+    const int b = W.b;
+    GEMB_TRY(katz(W, true, beta, J, P, scr0, scr1, scr2));       // scr0 = S^T P
+    GEMB_CUDA(cudaMemsetAsync(W.scal, 0, sizeof(double) * b, c->stream));
+    const int threads = (256 / b) * b > 0 ? (256 / b) * b : b;
+    coldiff_sumsq_kernel<<<c->sm_count * 4, threads, 0, c->stream>>>(W.rows, b, scr0, Qs, W.scal);
+    GEMB_CUDA(cudaGetLastError());
+    count_launch();
+    GEMB_TRY(comm_allreduce_f64(W, W.scal, b));
+    std::vector<double> rs(b);
+    GEMB_CUDA(cudaMemcpyAsync(rs.data(), W.scal, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
+    GEMB_CUDA(cudaStreamSynchronize(c->stream));
+    double rm = 0.0;
+    for (int j : cols) rm = std::max(rm, sqrt(rs[j]) / std::max(smax, 1e-300));
+    *out = (float)rm;
+    return GEMB_OK;
+}
+
+// ------------------------------------------------------------------------------------ general solver
+static int hope_general(HopeWork &W, const Opts &o, int d, float beta, int J, HopeResult &R) {
+    gemb_ctx *c = W.c;
+    const int b = W.b, k = d / 2;
+    float *V = W.buf[0], *U = W.buf[1], *Wk = W.buf[2], *T1 = W.buf[3], *T2 = W.buf[4];
+    R.algorithm = 1;
+    R.katz_terms = J;
+    GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)W.g->row0, T1));
+    GEMB_TRY(cholqr2(W, T1, T2, V));
+
+    std::vector<double> theta(b), theta_prev(b, 0.0);
+    for (int it = 1; it <= o.max_iters; it++) {
+        R.iters = it;
+        GEMB_TRY(katz(W, false, beta, J, V, U, T1, T2));              // U = S V
+        GEMB_TRY(gram_full(W, U, U, W.G));                            // T = U^T U
+        GEMB_CUDA(cudaMemcpyAsync(W.G2, W.G, sizeof(double) * b * b, cudaMemcpyDeviceToDevice, c->stream));
+        GEMB_TRY(c->t_dense.begin(c->stream));
+        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs));
+        GEMB_TRY(c->t_dense.end(c->stream));
+        GEMB_CUDA(cudaMemcpyAsync(theta.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        const double tmax = std::max(theta[b - 1], 1e-300);
+        double change = 0.0;
+        for (int j = b - k; j < b; j++) change = std::max(change, fabs(theta[j] - theta_prev[j]) / tmax);
+        R.change = change;
+        theta_prev = theta;
+        if (o.verbose)
+            fprintf(stderr, "[gemb_hope/general] it %d  sigma_max %.6g sigma_k %.6g  ritz change %.3g\n", it,
+                    sqrt(tmax), sqrt(std::max(theta[b - k], 0.0)), change);
+        if (it >= o.min_iters && change <= (double)o.tol) { R.converged = 1; break; }
+        if (it == o.max_iters) break;
+        // T1 = U Z Theta^-1/2: exactly orthonormal columns (Z diagonalises U^T U), ordered by sigma, so the
+        // next block S^T T1 ~ V Z Sigma has nearly orthogonal columns whatever the spread of sigma is
+        GEMB_TRY(c->t_dense.begin(c->stream));
+        ritz_maps_kernel<<<(b * b + 255) / 256, 256, 0, c->stream>>>(b, b, W.w, W.Z, W.M1, W.M2, -0.5, 0.5, 1e-10);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+        GEMB_TRY(apply_launch(c, W.rows, U, b, W.M1, b, b, T1, b));
+        GEMB_TRY(c->t_dense.end(c->stream));
+        GEMB_TRY(katz(W, true, beta, J, T1, Wk, U, T2));              // Wk = S^T T1   (U is scratch now)
+        GEMB_TRY(cholqr2(W, Wk, T1, V));                              // V = orth(S^T orth(S V))
+    }
+    R.sigma_max = sqrt(std::max(theta[b - 1], 0.0));
+
+    // extraction: X = [U Z_k theta^-1/4 | V Z_k theta^1/4]; U = S V (un-normalised), V orthonormal
+    R.Xd = T1;
+    if ((size_t)d > (size_t)b) {
+        GEMB_CUDA(cudaMalloc(&R.Xalloc, sizeof(float) * (size_t)std::max<int64_t>(W.rows, 1) * d));
+        R.Xd = R.Xalloc;
+    }
+    GEMB_TRY(c->t_dense.begin(c->stream));
+    ritz_maps_kernel<<<(b * k + 255) / 256, 256, 0, c->stream>>>(b, k, W.w, W.Z, W.M1, W.M2, -0.25, 0.25);
+    GEMB_CUDA(cudaGetLastError());
+    count_launch();
+    GEMB_TRY(apply_launch(c, W.rows, U, b, W.M1, k, k, R.Xd, d));
+    GEMB_TRY(apply_launch(c, W.rows, V, b, W.M2, k, k, R.Xd + k, d));
+    R.sig_dev = (float *)W.G2;  // G2 is free after eigh
+    sqrt_top_kernel<<<(k + 127) / 128, 128, 0, c->stream>>>(b, k, W.w, R.sig_dev);
+    GEMB_CUDA(cudaGetLastError());
+    count_launch();
+    GEMB_TRY(c->t_dense.end(c->stream));
+
+    if (o.compute_residual) {
+        // left vectors P = U Z theta^-1/2 (all b Ritz pairs), right Q sigma = V Z theta^1/2
+        ritz_maps_kernel<<<(b * b + 255) / 256, 256, 0, c->stream>>>(b, b, W.w, W.Z, W.M1, W.M2, -0.5, 0.5);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+        float *Pm = Wk, *Qs = nullptr, *Qalloc = nullptr, *STP = nullptr;
+        const size_t blk = sizeof(float) * (size_t)W.shard * b;
+        if (R.Xalloc) Qs = T1;
+        else { GEMB_CUDA(cudaMalloc(&Qalloc, blk ? blk : 4)); GEMB_CUDA(cudaMemsetAsync(Qalloc, 0, blk, c->stream)); Qs = Qalloc; }
+        GEMB_CUDA(cudaMalloc(&STP, blk ? blk : 4));
+        GEMB_CUDA(cudaMemsetAsync(STP, 0, blk, c->stream));
+        int s = apply_launch(c, W.rows, U, b, W.M1, b, b, Pm, b);
+        if (s == GEMB_OK) s = apply_launch(c, W.rows, V, b, W.M2, b, b, Qs, b);
+        std::vector<int> cols;
+        for (int j = b - k; j < b; j++) cols.push_back(j);
+        if (s == GEMB_OK) s = residual_check(W, beta, J, Pm, Qs, STP, U, T2, cols, R.sigma_max, &R.resid_max);
+        cudaFree(STP);
+        cudaFree(Qalloc);
+        if (s != GEMB_OK) return s;
+    }
+    return GEMB_OK;
+}
+
+// dst = orth(F) where Z (= W.Z, eigenvectors of the last Rayleigh-Ritz matrix) pre-rotates the columns:
+// F Z has nearly orthogonal columns (exactly, on an invariant subspace), so after the diagonal scaling
+// inside chol_inverse the Cholesky factorisation is well conditioned whatever the dynamic range of the
+// filter.  G' = Z^T (F^T F) Z,  G' = R^T R,  pass 1: tmp = F (Z R^-1);  pass 2: plain CholeskyQR.
+static int orth_rotated(HopeWork &W, const float *F, float *tmp, float *dst) {
+    gemb_ctx *c = W.c;
+    const int b = W.b;
+    GEMB_TRY(gram_full(W, F, F, W.G));
+    GEMB_TRY(c->t_dense.begin(c->stream));
+    GEMB_TRY(small_gemm_launch(c, b, W.G, 0, W.Z, W.Zs, nullptr));        // Zs = G Z
+    GEMB_TRY(small_gemm_launch(c, b, W.Z, 1, W.Zs, W.G, nullptr));        // G  = Z^T G Z
+    GEMB_TRY(chol_inverse_launch(c, b, W.G, W.Minv, W.rank_dev, W.G2));   // G2 = R^-1 (fp64)
+    GEMB_TRY(small_gemm_launch(c, b, W.Z, 0, W.G2, nullptr, W.M1));       // M1 = Z R^-1
+    GEMB_TRY(apply_launch(c, W.rows, F, b, W.M1, b, b, tmp, b));
+    GEMB_TRY(c->t_dense.end(c->stream));
+    GEMB_TRY(gram_full(W, tmp, tmp, W.G));
+    GEMB_TRY(cholqr_pass(W, W.G, tmp, dst));
+    return GEMB_OK;
+}
+
+// ------------------------------------------------------------------------------------ symmetric solver
+static inline double katz_f(double beta, double l) { return beta * l / (1.0 - beta * l); }
+
+static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double nrm, HopeResult &R) {
+    gemb_ctx *c = W.c;
+    const int b = W.b, k = d / 2;
+    R.algorithm = 2;
+    R.katz_terms = 0;
+    float *V = W.buf[0], *AV = W.buf[1];
+    float *pool[3] = {W.buf[2], W.buf[3], W.buf[4]};
+    const double bound = nrm * 1.02 + 1e-30;
+
+    GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)W.g->row0, pool[0]));
+    GEMB_TRY(cholqr2(W, pool[0], pool[1], V));
+    const int warm = 3;   // plain power steps V <- orth(A V) before the first Chebyshev filter
+
+    std::vector<double> lam(b), gval(b), th_sorted(b), th_prev(b, 0.0);
+    std::vector<int> order(b);
+    for (int it = 1; it <= o.max_iters; it++) {
+        R.iters = it;
+        // Rayleigh-Ritz on A
+        GEMB_TRY(dist_spmm(W, false, b, 1.f, V, nullptr, AV, true));
+        GEMB_TRY(gram_full(W, V, AV, W.G2));
+        symmetrize_kernel<<<(b * b + 255) / 256, 256, 0, c->stream>>>(b, W.G2);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+        GEMB_TRY(c->t_dense.begin(c->stream));
+        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs));
+        GEMB_TRY(c->t_dense.end(c->stream));
+        GEMB_CUDA(cudaMemcpyAsync(lam.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < b; i++) {
+            const double l = std::max(-bound, std::min(bound, lam[i]));  // Ritz values lie inside the spectrum
+            gval[i] = fabs(katz_f(beta, l));
+        }
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&](int a, int c2) { return gval[a] > gval[c2]; });   // descending |f|
+        for (int i = 0; i < b; i++) th_sorted[i] = gval[order[i]] * gval[order[i]];
+        const double tmax = std::max(th_sorted[0], 1e-300);
+        double change = 0.0;
+        for (int j = 0; j < k; j++) change = std::max(change, fabs(th_sorted[j] - th_prev[j]) / tmax);
+        R.change = change;
+        th_prev = th_sorted;
+        if (o.verbose)
+            fprintf(stderr, "[gemb_hope/symmetric] it %d  sigma_max %.6g sigma_k %.6g  ritz change %.3g\n", it,
+                    gval[order[0]], gval[order[k - 1]], change);
+        if (it >= o.min_iters && change <= (double)o.tol) { R.converged = 1; break; }
+        if (it == o.max_iters) break;
+
+        if (it <= warm) {                                              // A V is already there: one power step
+            GEMB_TRY(orth_rotated(W, AV, pool[0], V));
+            continue;
+        }
+        // damped set {l : |f(l)| < tau}, tau = smallest |f| in the block
+        const double tau = gval[order[b - 1]];
+        double hi = tau / ((double)beta * (1.0 + tau));
+        double lo = tau < 1.0 ? -tau / ((double)beta * (1.0 - tau)) : -bound;
+        lo = std::max(lo, -bound);
+        hi = std::min(hi, bound);
+        if (hi - lo < 2e-3 * bound) { const double mid = 0.5 * (hi + lo); lo = mid - 1e-3 * bound; hi = mid + 1e-3 * bound; }
+        const double e = 0.5 * (hi - lo), c0 = 0.5 * (hi + lo);
+        const double aL = lam[order[0]] >= c0 ? bound : -bound;       // normalise p(aL) = 1 at the dominant end
+        double sigma = e / (aL - c0);
+        const double tau2 = 2.0 / sigma;
+        // Y1 = (sigma/e) (A V - c0 V)  -- A V is the Rayleigh-Ritz product, no extra SpMM
+        float *prev = V, *cur = pool[0];
+        float *free_a = pool[1], *free_b = pool[2];
+        GEMB_TRY(axpby_launch(W, (float)(sigma / e), AV, (float)(-sigma * c0 / e), V, cur));
+        for (int i = 2; i <= o.cheb_degree; i++) {
+            const double sn = 1.0 / (tau2 - sigma);
+            float *nxt = free_a;
+            GEMB_TRY(dist_spmm3(W, false, b, (float)(2.0 * sn / e), cur, (float)(-2.0 * sn * c0 / e), true,
+                                (float)(-sigma * sn), prev, nxt, true));
+            sigma = sn;
+            // rotate: the old `prev` becomes free unless it is V (V must survive until the new basis exists)
+            float *old_prev = prev;
+            prev = cur;
+            cur = nxt;
+            if (old_prev == V) { free_a = free_b; free_b = nullptr; }
+            else { free_a = old_prev; }
+        }
+        // orthonormalise the filtered block into V; scratch = any block that is neither cur nor V
+        float *tmp = nullptr;
+        for (float *cand : {pool[0], pool[1], pool[2], AV})
+            if (cand != cur) { tmp = cand; break; }
+        GEMB_TRY(orth_rotated(W, cur, tmp, V));
+    }
+
+    // ---- extraction: top k by |f|, ascending sigma
+    std::vector<int> sel(order.begin(), order.begin() + k);
+    std::reverse(sel.begin(), sel.end());                             // ascending |f|
+    std::vector<double> Zh((size_t)b * b);
+    GEMB_CUDA(cudaMemcpyAsync(Zh.data(), W.Z, sizeof(double) * b * b, cudaMemcpyDeviceToHost, c->stream));
+    GEMB_CUDA(cudaStreamSynchronize(c->stream));
+    std::vector<float> M1((size_t)b * k), M2((size_t)b * k), sig(k);
+    for (int j = 0; j < k; j++) {
+        const int col = sel[j];
+        const double l = std::max(-bound, std::min(bound, lam[col]));
+        const double f = katz_f(beta, l), sg = fabs(f), rt = sqrt(sg);
+        sig[j] = (float)sg;
+        for (int i = 0; i < b; i++) {
+            const double z = Zh[(size_t)i * b + col];
+            M2[(size_t)i * k + j] = (float)(z * rt);
+            M1[(size_t)i * k + j] = (float)((f < 0 ? -z : z) * rt);
+        }
+    }
+    R.sigma_max = gval[order[0]];
+    GEMB_CUDA(cudaMemcpyAsync(W.M1, M1.data(), sizeof(float) * b * k, cudaMemcpyHostToDevice, c->stream));
+    GEMB_CUDA(cudaMemcpyAsync(W.M2, M2.data(), sizeof(float) * b * k, cudaMemcpyHostToDevice, c->stream));
+    R.sig_dev = (float *)W.G2;
+    GEMB_CUDA(cudaMemcpyAsync(R.sig_dev, sig.data(), sizeof(float) * k, cudaMemcpyHostToDevice, c->stream));
+    GEMB_CUDA(cudaStreamSynchronize(c->stream));                      // host staging vectors go out of scope
+    R.Xd = pool[0];
+    if ((size_t)d > (size_t)b) {
+        GEMB_CUDA(cudaMalloc(&R.Xalloc, sizeof(float) * (size_t)std::max<int64_t>(W.rows, 1) * d));
+        R.Xd = R.Xalloc;
+    }
+    GEMB_TRY(c->t_dense.begin(c->stream));
+    GEMB_TRY(apply_launch(c, W.rows, V, b, W.M1, k, k, R.Xd, d));
+    GEMB_TRY(apply_launch(c, W.rows, V, b, W.M2, k, k, R.Xd + k, d));
+    GEMB_TRY(c->t_dense.end(c->stream));
+
+    if (o.compute_residual) {
+        // check the triplets against the Katz operator itself: || S^T u - sigma v || / sigma_max
+        const int J = katz_terms_for(beta, nrm, o.katz_tol);
+        std::vector<float> MP((size_t)b * b, 0.f), MQ((size_t)b * b, 0.f);
+        for (int col = 0; col < b; col++) {
+            const double l = std::max(-bound, std::min(bound, lam[col]));
+            const double f = katz_f(beta, l);
+            for (int i = 0; i < b; i++) {
+                const double z = Zh[(size_t)i * b + col];
+                MP[(size_t)i * b + col] = (float)(f < 0 ? -z : z);    // u = sign(f) v
+                MQ[(size_t)i * b + col] = (float)(z * fabs(f));       // v sigma
+            }
+        }
+        float *dMP = nullptr, *dMQ = nullptr, *P = nullptr, *Q = nullptr, *STP = nullptr;
+        const size_t blk = sizeof(float) * (size_t)W.shard * b;
+        GEMB_CUDA(cudaMalloc(&dMP, sizeof(float) * b * b));
+        GEMB_CUDA(cudaMalloc(&dMQ, sizeof(float) * b * b));
+        GEMB_CUDA(cudaMalloc(&P, blk ? blk : 4));
+        GEMB_CUDA(cudaMalloc(&Q, blk ? blk : 4));
+        GEMB_CUDA(cudaMalloc(&STP, blk ? blk : 4));
+        GEMB_CUDA(cudaMemsetAsync(P, 0, blk, c->stream));
+        GEMB_CUDA(cudaMemsetAsync(Q, 0, blk, c->stream));
+        GEMB_CUDA(cudaMemsetAsync(STP, 0, blk, c->stream));
+        GEMB_CUDA(cudaMemcpyAsync(dMP, MP.data(), sizeof(float) * b * b, cudaMemcpyHostToDevice, c->stream));
+        GEMB_CUDA(cudaMemcpyAsync(dMQ, MQ.data(), sizeof(float) * b * b, cudaMemcpyHostToDevice, c->stream));
+        int s = apply_launch(c, W.rows, V, b, dMP, b, b, P, b);
+        if (s == GEMB_OK) s = apply_launch(c, W.rows, V, b, dMQ, b, b, Q, b);
+        if (s == GEMB_OK) s = residual_check(W, beta, J, P, Q, STP, AV, pool[1], sel, R.sigma_max, &R.resid_max);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(dMP); cudaFree(dMQ); cudaFree(P); cudaFree(Q); cudaFree(STP);
+        if (s != GEMB_OK) return s;
+    }
+    return GEMB_OK;
+}
+
 }  // namespace gemb
 
 using namespace gemb;
@@ -155,10 +554,7 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     GEMB_ARG(!stats || stats->struct_size == sizeof(gemb_hope_stats), "stats.struct_size");
     gemb_ctx *c = g->ctx;
     GEMB_CUDA(cudaSetDevice(c->device));
-    gemb_hope_opts o;
-    memset(&o, 0, sizeof o);
-    o.oversample = 16; o.max_iters = 30; o.min_iters = 2; o.tol = 1e-6f; o.katz_terms = 0;
-    o.katz_tol = 1e-7f; o.seed = 1234; o.compute_residual = 0; o.verbose = 0;
+    Opts o;
     if (uo) {
         GEMB_ARG(uo->struct_size == sizeof(gemb_hope_opts), "opts.struct_size");
         if (uo->oversample >= 0) o.oversample = uo->oversample;
@@ -170,7 +566,15 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         if (uo->seed) o.seed = uo->seed;
         o.compute_residual = uo->compute_residual;
         o.verbose = uo->verbose;
+        GEMB_ARG(uo->algorithm >= 0 && uo->algorithm <= 2, "opts.algorithm");
+        o.algorithm = uo->algorithm;
+        if (uo->cheb_degree >= 2) o.cheb_degree = uo->cheb_degree;
     }
+    if (o.algorithm == 2 && !g->symmetric) {
+        set_error("algorithm=2 (Chebyshev on A) needs a symmetric shard (upload with indptr_t = NULL)");
+        return GEMB_ERR_ARG;
+    }
+    const int algo = o.algorithm ? o.algorithm : (g->symmetric ? 2 : 1);
     const int k = d / 2;
     GEMB_ARG((int64_t)k <= g->n, "d/2 must not exceed the number of nodes");
     int64_t bb = std::min<int64_t>(g->n, (int64_t)k + o.oversample);
@@ -202,155 +606,23 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     GEMB_CUDA(cudaEventCreate(&ev1));
     GEMB_CUDA(cudaEventRecord(ev0, c->stream));
 
-    float *V = W.buf[0], *U = W.buf[1], *Wk = W.buf[2], *T1 = W.buf[3], *T2 = W.buf[4];
-    float norm2 = 0.f;
+    double nrm = 0.0;
     int J = o.katz_terms;
-
-    // ---- ||A||_2 by power iteration on A^T A with a 4-column block (only when J is automatic)
-    if (J <= 0) {
-        const int pw = 4;
-        float *x = T1, *y = T2, *z = Wk;  // reuse (width 4 slices of the big buffers)
-        GEMB_TRY(randn_launch(c, W.rows, pw, o.seed ^ 0x5bd1e995u, (uint64_t)g->row0, x));
-        double est = 0.0, prev = -1.0;
-        for (int it = 0; it < 16; it++) {
-            double h[2];
-            GEMB_TRY(sumsq_launch(c, W.rows * pw, x, W.scal));
-            const float *xf = x;
-            if (c->nranks > 1) {
-                // shard stride for width-4 gather = n_shard * 4 floats
-                NcclApi *api = nccl_api();
-                if (!api) return GEMB_ERR_NCCL;
-                ncclResult_t r = api->AllGather(x, W.full, (size_t)W.shard * pw, ncclFloat, (ncclComm_t)c->comm, c->stream);
-                if (r != ncclSuccess) { set_error("ncclAllGather: %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
-                xf = W.full;
-            }
-            GEMB_TRY(spmm_launch(c, g->A, W.rows, pw, 1.f, xf, nullptr, y));
-            const float *yf = y;
-            if (c->nranks > 1) {
-                NcclApi *api = nccl_api();
-                ncclResult_t r = api->AllGather(y, W.full, (size_t)W.shard * pw, ncclFloat, (ncclComm_t)c->comm, c->stream);
-                if (r != ncclSuccess) { set_error("ncclAllGather: %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
-                yf = W.full;
-            }
-            GEMB_TRY(spmm_launch(c, g->AT, W.rows, pw, 1.f, yf, nullptr, z));
-            W.spmm_all += 2;
-            GEMB_TRY(sumsq_launch(c, W.rows * pw, z, W.scal + 1));
-            GEMB_TRY(comm_allreduce_f64(W, W.scal, 2));
-            GEMB_CUDA(cudaMemcpyAsync(h, W.scal, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-            GEMB_CUDA(cudaStreamSynchronize(c->stream));
-            if (!(h[0] > 0.0) || !(h[1] > 0.0)) { est = 0.0; break; }  // A^T A x = 0: nilpotent-ish / empty
-            est = sqrt(sqrt(h[1] / h[0]));   // ||A^T A x|| / ||x|| -> sigma_max^2
-            GEMB_TRY(scale_launch(c, W.rows * pw, (float)(1.0 / sqrt(h[1])), z));
-            std::swap(x, z);
-            if (prev > 0 && fabs(est - prev) <= 1e-3 * est && it >= 3) break;
-            prev = est;
-        }
-        norm2 = (float)est;
-        const double x1 = (double)beta * est * 1.02;
-        if (x1 >= 1.0) {
+    if (J <= 0 || algo == 2) {
+        GEMB_TRY(estimate_norm2(W, o.seed, W.buf[3], W.buf[4], W.buf[2], &nrm));
+        if ((double)beta * nrm * 1.02 >= 1.0) {
             set_error("beta * ||A||_2 = %.4g >= 1: the Katz series (I - beta A)^-1 beta A does not converge; "
-                      "choose beta < %.4g", (double)beta * est, 1.0 / est);
+                      "choose beta < %.4g", (double)beta * nrm, 1.0 / nrm);
             cudaEventDestroy(ev0); cudaEventDestroy(ev1);
             return GEMB_ERR_DIVERGE;
         }
-        if (x1 <= 1e-30) J = 1;
-        else J = (int)ceil(log((double)o.katz_tol) / log(x1));
-        // a nilpotent A (e.g. a DAG) can have ||A||_2 large but finite series; the bound still holds
-        J = std::max(1, std::min(J, 4096));
-        // buffers were used as scratch with width 4: re-zero the touched prefixes (padding rows)
-        for (int i = 2; i < 5; i++) GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));
+        if (J <= 0) J = katz_terms_for(beta, nrm, o.katz_tol);
+        for (int i = 2; i < 5; i++) GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));  // width-4 scratch
     }
 
-    // ---- start block
-    GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)g->row0, T1));
-    GEMB_TRY(gram_full(W, T1, T1, W.G));
-    GEMB_TRY(cholqr_pass(W, W.G, T1, T2));
-    GEMB_TRY(gram_full(W, T2, T2, W.G));
-    GEMB_TRY(cholqr_pass(W, W.G, T2, V));
-
-    std::vector<double> theta(b), theta_prev(b, 0.0);
-    int iters = 0, converged = 0;
-    double change = 0.0;
-    for (int it = 1; it <= o.max_iters; it++) {
-        iters = it;
-        GEMB_TRY(katz(W, false, beta, J, V, U, T1, T2));              // U = S V
-        GEMB_TRY(gram_full(W, U, U, W.G));                            // T = U^T U
-        GEMB_CUDA(cudaMemcpyAsync(W.G2, W.G, sizeof(double) * b * b, cudaMemcpyDeviceToDevice, c->stream));
-        GEMB_TRY(c->t_dense.begin(c->stream));
-        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs));
-        GEMB_TRY(c->t_dense.end(c->stream));
-        GEMB_CUDA(cudaMemcpyAsync(theta.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
-        GEMB_CUDA(cudaStreamSynchronize(c->stream));
-        const double tmax = std::max(theta[b - 1], 1e-300);
-        change = 0.0;
-        for (int j = b - k; j < b; j++) change = std::max(change, fabs(theta[j] - theta_prev[j]) / tmax);
-        theta_prev = theta;
-        if (o.verbose)
-            fprintf(stderr, "[gemb_hope] it %d  sigma_max %.6g sigma_k %.6g  ritz change %.3g\n", it,
-                    sqrt(tmax), sqrt(std::max(theta[b - k], 0.0)), change);
-        if (it >= o.min_iters && change <= (double)o.tol) { converged = 1; break; }
-        if (it == o.max_iters) break;
-        GEMB_TRY(cholqr_pass(W, W.G, U, T1));                         // T1 = orth(U) (one pass)
-        GEMB_TRY(katz(W, true, beta, J, T1, Wk, U, T2));              // Wk = S^T T1   (U is scratch now)
-        GEMB_TRY(gram_full(W, Wk, Wk, W.G));
-        GEMB_TRY(cholqr_pass(W, W.G, Wk, T1));
-        GEMB_TRY(gram_full(W, T1, T1, W.G));
-        GEMB_TRY(cholqr_pass(W, W.G, T1, V));                         // V = orth(S^T orth(S V))
-    }
-
-    // ---- extraction: X = [U Z_k theta^-1/4 | V Z_k theta^1/4]; U = S V (un-normalised), V orthonormal
-    float *Xd = T1;  // n_shard x d fits: d = 2k <= ... ensure capacity
-    float *Xalloc = nullptr;
-    if ((size_t)d > (size_t)b) {
-        GEMB_CUDA(cudaMalloc(&Xalloc, sizeof(float) * (size_t)std::max<int64_t>(W.rows, 1) * d));
-        Xd = Xalloc;
-    }
-    GEMB_TRY(c->t_dense.begin(c->stream));
-    ritz_maps_kernel<<<(b * k + 255) / 256, 256, 0, c->stream>>>(b, k, W.w, W.Z, W.M1, W.M2, -0.25, 0.25);
-    GEMB_CUDA(cudaGetLastError());
-    count_launch();
-    GEMB_TRY(apply_launch(c, W.rows, U, b, W.M1, k, k, Xd, d));
-    GEMB_TRY(apply_launch(c, W.rows, V, b, W.M2, k, k, Xd + k, d));
-    float *sig_dev = (float *)W.Minv;  // reuse
-    sqrt_top_kernel<<<(k + 127) / 128, 128, 0, c->stream>>>(b, k, W.w, sig_dev);
-    GEMB_CUDA(cudaGetLastError());
-    count_launch();
-    GEMB_TRY(c->t_dense.end(c->stream));
-
-    float resid_max = -1.f;
-    if (o.compute_residual) {
-        // left vectors P = U Z theta^-1/2 (all b Ritz pairs), right Q = V Z ; check S^T P = Q sigma
-        ritz_maps_kernel<<<(b * b + 255) / 256, 256, 0, c->stream>>>(b, b, W.w, W.Z, W.M1, W.M2, -0.5, 0.5);
-        GEMB_CUDA(cudaGetLastError());
-    count_launch();
-        float *Pm = Wk, *Qs = (Xalloc ? T1 : nullptr);
-        float *Qalloc = nullptr;
-        if (!Qs) { GEMB_CUDA(cudaMalloc(&Qalloc, blk ? blk : 4)); GEMB_CUDA(cudaMemsetAsync(Qalloc, 0, blk, c->stream)); Qs = Qalloc; }
-        GEMB_TRY(apply_launch(c, W.rows, U, b, W.M1, b, b, Pm, b));          // P
-        GEMB_TRY(apply_launch(c, W.rows, V, b, W.M2, b, b, Qs, b));          // Q sigma  (theta^1/2 = sigma)
-        // S^T P -> needs scratch: U is still needed? (X already extracted) -> reuse U and T2
-        float *STP = nullptr;
-        GEMB_CUDA(cudaMalloc(&STP, blk ? blk : 4));
-        GEMB_CUDA(cudaMemsetAsync(STP, 0, blk, c->stream));
-        float *scr1 = U, *scr2 = T2;
-        int s = katz(W, true, beta, J, Pm, STP, scr1, scr2);
-        if (s != GEMB_OK) { cudaFree(STP); cudaFree(Qalloc); cudaFree(Xalloc); return s; }
-        GEMB_CUDA(cudaMemsetAsync(W.scal, 0, sizeof(double) * b, c->stream));
-        const int threads = (256 / b) * b > 0 ? (256 / b) * b : b;
-        coldiff_sumsq_kernel<<<c->sm_count * 4, threads, 0, c->stream>>>(W.rows, b, STP, Qs, W.scal);
-        GEMB_CUDA(cudaGetLastError());
-    count_launch();
-        GEMB_TRY(comm_allreduce_f64(W, W.scal, b));
-        std::vector<double> rs(b);
-        GEMB_CUDA(cudaMemcpyAsync(rs.data(), W.scal, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
-        GEMB_CUDA(cudaStreamSynchronize(c->stream));
-        const double smax = sqrt(std::max(theta[b - 1], 1e-300));
-        double rm = 0.0;
-        for (int j = b - k; j < b; j++) rm = std::max(rm, sqrt(rs[j]) / smax);
-        resid_max = (float)rm;
-        cudaFree(STP);
-        cudaFree(Qalloc);
-    }
+    HopeResult R;
+    int s = (algo == 2) ? hope_symmetric(W, o, d, beta, nrm, R) : hope_general(W, o, d, beta, J, R);
+    if (s != GEMB_OK) { cudaFree(R.Xalloc); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return s; }
 
     GEMB_CUDA(cudaEventRecord(ev1, c->stream));
     GEMB_CUDA(cudaEventSynchronize(ev1));
@@ -362,21 +634,22 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         cudaEvent_t e2, e3;
         GEMB_CUDA(cudaEventCreate(&e2)); GEMB_CUDA(cudaEventCreate(&e3));
         GEMB_CUDA(cudaEventRecord(e2, c->stream));
-        if (X_out) GEMB_CUDA(cudaMemcpyAsync(X_out, Xd, sizeof(float) * (size_t)W.rows * d, cudaMemcpyDeviceToHost, c->stream));
-        if (sigma_out) GEMB_CUDA(cudaMemcpyAsync(sigma_out, sig_dev, sizeof(float) * k, cudaMemcpyDeviceToHost, c->stream));
+        if (X_out) GEMB_CUDA(cudaMemcpyAsync(X_out, R.Xd, sizeof(float) * (size_t)W.rows * d, cudaMemcpyDeviceToHost, c->stream));
+        if (sigma_out) GEMB_CUDA(cudaMemcpyAsync(sigma_out, R.sig_dev, sizeof(float) * k, cudaMemcpyDeviceToHost, c->stream));
         GEMB_CUDA(cudaEventRecord(e3, c->stream));
         GEMB_CUDA(cudaEventSynchronize(e3));
         float ms = 0.f; cudaEventElapsedTime(&ms, e2, e3); d2h_ms = ms;
         cudaEventDestroy(e2); cudaEventDestroy(e3);
     }
-    cudaFree(Xalloc);
+    cudaFree(R.Xalloc);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
 
     if (stats) {
-        stats->iters = iters;
-        stats->katz_terms = J;
+        stats->iters = R.iters;
+        stats->katz_terms = R.katz_terms;
         stats->block = b;
-        stats->converged = converged;
+        stats->converged = R.converged;
+        stats->algorithm = R.algorithm;
         stats->spmm_count = W.spmm_wide;   /* block-width sweeps (norm estimation excluded) */
         stats->spmm_ms = c->t_spmm.total_ms();
         const double nnz = (double)g->A.nnz;
@@ -387,9 +660,9 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         stats->total_ms = total_ms;
         stats->h2d_ms = 0.0;
         stats->d2h_ms = d2h_ms;
-        stats->norm2_A = norm2;
-        stats->ritz_change = (float)change;
-        stats->resid_max = resid_max;
+        stats->norm2_A = (float)nrm;
+        stats->ritz_change = (float)R.change;
+        stats->resid_max = R.resid_max;
     }
     return GEMB_OK;
 }

@@ -8,7 +8,8 @@ libgemb200.so (CUDA, sm_100a); there is no CPU path -- without a GPU learn_embed
 RuntimeError.
 
 Extra, optional hyper-parameters (defaults keep reference call sites working unchanged):
-    tol, max_iters, min_iters, oversample, katz_terms, katz_tol, seed, compute_residual, verbose
+    tol, max_iters, min_iters, oversample, katz_terms, katz_tol, seed, compute_residual, verbose,
+    algorithm (0 auto / 1 general / 2 symmetric-Chebyshev), cheb_degree
         -> gemb_hope_opts (include/gemb200.h)
     device (int), dtype (np.float32 default | np.float64)
 `graph` may also be a scipy.sparse matrix or a gem_b200.graph.HostCSR (rows = 0..n-1) so that
@@ -21,7 +22,7 @@ from gem_b200 import graph as _graph
 from gem_b200.embedding.static_graph_embedding import StaticGraphEmbedding
 
 _OPT_KEYS = ('tol', 'max_iters', 'min_iters', 'oversample', 'katz_terms', 'katz_tol', 'seed',
-             'compute_residual', 'verbose')
+             'compute_residual', 'verbose', 'algorithm', 'cheb_degree')
 
 
 class HOPE(StaticGraphEmbedding):
@@ -76,8 +77,8 @@ class HOPE(StaticGraphEmbedding):
         # hope.py:38-40 prints ||U S V^T - S||_F, which needs the dense n x n S; the part that is
         # computable without S is reported instead.
         if getattr(self, '_verbose', 0):
-            print('HOPE: %d iterations, J=%d Katz terms, block %d, ritz change %.3g' %
-                  (st['iters'], st['katz_terms'], st['block'], st['ritz_change']))
+            print('HOPE: algorithm %d, %d iterations, J=%d Katz terms, block %d, ritz change %.3g' %
+                  (st['algorithm'], st['iters'], st['katz_terms'], st['block'], st['ritz_change']))
         return self._X
 
     def get_edge_weight(self, i, j):

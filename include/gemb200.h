@@ -80,9 +80,16 @@ int gemb_graph_free(gemb_graph *g);
 int gemb_spmm(gemb_graph *g, int transpose, int b, float alpha, const float *X, const float *X0,
               float *Y);
 
+/* Test hook for the tensor-core contraction: G (b1 x b2, fp64, row-major) = P^T Q over n rows; P, Q host
+ * fp32 row-major (Q == NULL means Q = P).  use_tensor_cores: 1 = tcgen05 kernel (GEMB_ERR_UNSUPPORTED if the
+ * shape does not fit it), 0 = CUDA-core fp32 kernel. */
+int gemb_gram(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, int use_tensor_cores,
+              double *G_out);
+
 /* ---- HOPE.  Replaces hope.py:29-36: S = (I - beta A)^-1 beta A is never formed; its top
  * k = d/2 singular triplets come from a block subspace iteration with Rayleigh-Ritz whose
- * operator applications are Katz/Horner sweeps of CSR SpMM.  Output convention = the reference:
+ * operator applications are CSR SpMM sweeps (Katz/Horner sweeps of S and S^T in general; a Chebyshev
+ * filter in A itself when A is symmetric, since then S = f(A)).  Output convention = the reference:
  * X = [U sqrt(Sigma) | V sqrt(Sigma)], sigma ASCENDING (scipy svds order). */
 typedef struct {
     uint32_t struct_size;  /* = sizeof(gemb_hope_opts) */
@@ -96,6 +103,10 @@ typedef struct {
     uint64_t seed;         /* start block, default 1234 */
     int32_t compute_residual; /* 1: one extra Katz application to report ||S^T u - sigma v|| */
     int32_t verbose;
+    int32_t algorithm;     /* 0 = auto (2 when the shard is symmetric, else 1); 1 = subspace iteration on
+                              S^T S through Katz sweeps (any A); 2 = Chebyshev-filtered subspace iteration on
+                              A itself, S = f(A) (symmetric A only) */
+    int32_t cheb_degree;   /* filter degree per outer iteration of algorithm 2, default 8 */
 } gemb_hope_opts;
 
 typedef struct {
@@ -104,6 +115,7 @@ typedef struct {
     int32_t katz_terms;    /* J actually used */
     int32_t block;         /* b */
     int32_t converged;
+    int32_t algorithm;     /* 1 or 2: the solver that ran */
     int64_t spmm_count;    /* SpMM sweeps executed (all of width `block` except norm estimation) */
     double spmm_ms;        /* sum of CUDA-event durations of the block-width SpMM launches */
     double spmm_bytes;     /* algorithmic bytes of ONE block-width sweep: 8*nnz + 4*(n+1) + 8*n*b

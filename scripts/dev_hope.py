@@ -12,6 +12,8 @@ ap.add_argument('--tol', type=float, default=1e-4)
 ap.add_argument('--max-iters', type=int, default=30)
 ap.add_argument('--reps', type=int, default=3)
 ap.add_argument('--rmat', type=int, default=0)
+ap.add_argument('--algorithm', type=int, default=0)
+ap.add_argument('--cheb-degree', type=int, default=0)
 a = ap.parse_args()
 t = time.time()
 csr = synth.rmat(scale=a.rmat) if a.rmat else synth.sbm(n=a.n)
@@ -22,7 +24,7 @@ g = _native.DeviceGraph(ctx, csr.n, csr.indptr, csr.indices, None)
 print('upload s', round(time.time() - t, 3), flush=True)
 for r in range(a.reps):
     t = time.time()
-    X, sig, st = g.hope(a.d, a.beta, tol=a.tol, max_iters=a.max_iters, want_output=(r == a.reps - 1), verbose=(r == 0),
+    X, sig, st = g.hope(a.d, a.beta, tol=a.tol, max_iters=a.max_iters, want_output=(r == a.reps - 1), verbose=(r == 0), algorithm=a.algorithm, cheb_degree=a.cheb_degree,
                         compute_residual=int(r == a.reps - 1))
     wall = time.time() - t
     st['wall_s'] = wall

@@ -1,0 +1,76 @@
+"""Multi-GPU equivalence check, launched with torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/mgpu_check.py
+Checks (rank 0 prints one JSON line, exit code != 0 on failure):
+  * HOPE on a row-sharded CSR (NCCL all-gather per SpMM, all-reduce per Gram) == the same solve on one GPU
+    (sigma rtol 2e-5, reconstruction 2e-4), for the symmetric-Chebyshev and the general solver;
+  * node2vec: walk shards are the slices of the single-GPU walk matrix (bit-exact); the data-parallel SGNS
+    (delta all-reduce per epoch) learns the SBM communities (nearest-neighbour purity)."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+import numpy as np
+import torch
+import torch.distributed as dist
+from gem_b200 import _native, synth, dist as gd, graph as hg
+
+rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+ctx = _native.Context(local)
+gd.init_comm_from_torch(ctx, dist, rank, world)
+res = {'world': world}
+ok = True
+
+csr = synth.sbm(n=61_020, block=1017, seed=3)      # 61020 = 60 x 1017: not a multiple of 8 -> padded last shard
+d, beta = 32, 0.01
+r0, ip, ix, _ = csr.row_shard(rank, world)
+gsh = _native.DeviceGraph(ctx, csr.n, ip, ix, None, row0=r0)
+for algo in (2, 1):
+    Xs, sig, st = gsh.hope(d, beta, tol=1e-7, max_iters=60, min_iters=4, algorithm=algo, compute_residual=1)
+    parts = [None] * world
+    dist.all_gather_object(parts, Xs)
+    if rank == 0:
+        X = np.concatenate(parts)[:csr.n]
+        c1 = _native.Context(local)
+        g1 = _native.DeviceGraph(c1, csr.n, csr.indptr, csr.indices, None)
+        X1, sig1, st1 = g1.hope(d, beta, tol=1e-7, max_iters=60, min_iters=4, algorithm=algo, compute_residual=1)
+        g1.free(); c1.close()
+        import hope_oracle as ho
+        serr = float(np.abs(sig / sig1 - 1).max()); rec = float(ho.recon_rel_err(X, X1))
+        res['hope_algo%d' % algo] = dict(sigma_rel=serr, recon=rec, iters=(st['iters'], st1['iters']), resid=(st['resid_max'], st1['resid_max']),
+                                         comm_ms=st['comm_ms'], spmm_ms=st['spmm_ms'], total_ms=st['total_ms'])
+        ok &= serr < 2e-5 and rec < 2e-3 and st['resid_max'] < 5e-3
+gsh.free()
+
+# node2vec
+nids = np.arange(csr.n, dtype=np.int32)
+gfull = _native.DeviceGraph(ctx, csr.n, csr.indptr, csr.indices, None)
+tot = csr.n * 3
+w0, w1 = gd.walk_range(tot, rank, world)
+Wm, _ = gfull.n2v_walks(nids, 20, 3, seed=5, w_begin=w0, w_end=w1)
+if rank == 0:
+    Wall, _ = gfull.n2v_walks(nids, 20, 3, seed=5)
+    same = bool(np.array_equal(Wm, Wall[w0:w1]))
+    res['walk_shard_bit_exact'] = same
+    ok &= same
+X, st = gfull.node2vec(nids, 32, 40, 5, 5, 1, seed=9)
+Xs = [None] * world
+dist.all_gather_object(Xs, X[:2000].copy())
+if rank == 0:
+    res['n2v_replicas_identical'] = bool(all(np.array_equal(Xs[0], x) for x in Xs))
+    lab = np.arange(csr.n) // 1017
+    sub = np.arange(0, 6102)
+    Xn = X[sub] / (np.linalg.norm(X[sub], axis=1, keepdims=True) + 1e-12)
+    S = Xn @ Xn.T; np.fill_diagonal(S, -np.inf)
+    nn = np.argsort(-S, axis=1)[:, :10]
+    pur = float(np.mean(lab[sub][nn] == lab[sub][:, None]))
+    res['n2v_purity'] = pur; res['n2v_stats'] = {k: st[k] for k in ('sgns_ms', 'comm_ms', 'pairs', 'n_tokens')}
+    ok &= res['n2v_replicas_identical'] and pur > 0.8
+gfull.free(); ctx.close()
+flag = torch.tensor([1 if ok else 0], device='cuda')
+dist.broadcast(flag, src=0)
+if rank == 0:
+    res['ok'] = bool(ok)
+    print(json.dumps(res), flush=True)
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)

@@ -27,7 +27,7 @@ def test_exports_match_header(native_lib):
 
 def test_struct_sizes_are_stable(native_lib):
     from gem_b200 import _native
-    assert ctypes.sizeof(_native.HopeOpts) == 48
+    assert ctypes.sizeof(_native.HopeOpts) == 56
     assert ctypes.sizeof(_native.HopeStats) == 104
     assert ctypes.sizeof(_native.N2VStats) == 120
 

@@ -42,12 +42,15 @@ def test_karate_golden(gpu_ctx, hope_oracle):
     assert abs(A[3, 5] - np.dot(X[3, :2], X[5, 2:])) < 1e-7 and A[4, 4] == 0
 
 
-def test_sbm1024_golden(gpu_ctx, hope_oracle):
+@pytest.mark.parametrize('algorithm', [1, 2])
+def test_sbm1024_golden(gpu_ctx, hope_oracle, algorithm):
+    """algorithm 1 = subspace iteration on S^T S (Katz sweeps); 2 = Chebyshev filter on A (S = f(A), symmetric A)."""
     ho = hope_oracle
     G, z = load_sbm1024_nx()
     gold = z['hope_golden']
-    m = _fresh_hope(d=256, beta=0.01, oversample=128, tol=1e-9, max_iters=400, min_iters=8)
+    m = _fresh_hope(d=256, beta=0.01, oversample=128, tol=1e-9, max_iters=400, min_iters=8, algorithm=algorithm)
     X = m.learn_embedding(graph=G, is_weighted=True, no_python=True)
+    assert m.stats['algorithm'] == algorithm
     assert abs(np.mean(gold - X)) < 1e-3                                   # tests/test_sbm.py:94
     sg, sx = ho.sigma_from_embedding(gold), np.asarray(m._sigma, dtype=np.float64)
     assert np.allclose(sx, sg, rtol=1e-4), np.abs(sx / sg - 1).max()
@@ -58,31 +61,57 @@ def test_sbm1024_golden(gpu_ctx, hope_oracle):
     assert ho.recon_rel_err(X, gold) < 5e-2      # bulk singular values are nearly degenerate at the cut
 
 
-@pytest.mark.parametrize('name,recon_tol', [('karate_d16', RECON_TOL), ('sbm1024_d16', 2e-3),
-                                            ('randw200_d32', RECON_TOL)])
-def test_against_reference_class_outputs(gpu_ctx, hope_oracle, name, recon_tol):
+@pytest.mark.parametrize('name,recon_tol,algorithm', [('karate_d16', RECON_TOL, 0), ('sbm1024_d16', 2e-3, 1),
+                                                      ('sbm1024_d16', 2e-3, 2), ('randw200_d32', RECON_TOL, 0)])
+def test_against_reference_class_outputs(gpu_ctx, hope_oracle, name, recon_tol, algorithm):
     ho = hope_oracle
     z = np.load(golden_path('ref_hope_%s.npz' % name))
     G = nx_from_npz(z)
     d, beta, Xref = int(z['d']), float(z['beta']), z['X']
-    m = _fresh_hope(d=d, beta=beta, oversample=64, tol=1e-10, max_iters=300, min_iters=6, compute_residual=1)
+    m = _fresh_hope(d=d, beta=beta, oversample=64, tol=1e-10, max_iters=300, min_iters=6, compute_residual=1,
+                    algorithm=algorithm)
     X = m.learn_embedding(graph=G)
+    assert m.stats['algorithm'] == (algorithm or 1)          # directed inputs take the general solver
     assert np.allclose(m._sigma, ho.sigma_from_embedding(Xref), rtol=SIG_RTOL, atol=1e-9)
     assert ho.recon_rel_err(X, Xref) < recon_tol, ho.recon_rel_err(X, Xref)
     assert m.stats['resid_max'] < 1e-3
 
 
-def test_repeated_singular_values_cliques(gpu_ctx, hope_oracle):
-    """Ring of cliques: exactly repeated sigma -> vectors are not unique; sigma and residuals are."""
+@pytest.mark.parametrize('algorithm', [1, 2])
+def test_repeated_singular_values_cliques(gpu_ctx, hope_oracle, algorithm):
+    """Ring of cliques: exactly repeated sigma (and negative eigenvalues of A) -> vectors are not unique;
+    sigma and residuals are."""
     ho = hope_oracle
     z = np.load(golden_path('ref_hope_cliques_d24.npz'))
     G = nx_from_npz(z)
-    m = _fresh_hope(d=24, beta=0.05, oversample=40, tol=1e-10, max_iters=200, compute_residual=1)
+    m = _fresh_hope(d=24, beta=0.05, oversample=40, tol=1e-10, max_iters=200, compute_residual=1, algorithm=algorithm)
     X = m.learn_embedding(graph=G)
     assert np.allclose(m._sigma, ho.sigma_from_embedding(z['X']), rtol=SIG_RTOL)
     A = ho.adjacency_from_nx(G)
     r1, r2, _, _ = ho.svd_residuals(A, 0.05, X, ho.katz_terms_needed(A, 0.05, 1e-14))
     assert max(r1.max(), r2.max()) < 2e-5
+
+
+def test_symmetric_solver_refuses_directed_input(gpu_ctx):
+    m = _fresh_hope(d=4, beta=0.01, algorithm=2)
+    with pytest.raises(RuntimeError, match='symmetric'):
+        m.learn_embedding(graph=load_karate_nx())
+
+
+def test_bipartite_negative_spectrum(gpu_ctx, hope_oracle):
+    """Bipartite graph: spectrum symmetric about 0, so |f(l)| ranks +l above -l but both ends matter."""
+    import networkx as nx
+    ho = hope_oracle
+    B = nx.DiGraph(nx.complete_bipartite_graph(9, 14))
+    B.add_edges_from([(0, 1), (1, 0), (10, 11), (11, 10)])      # break exact bipartiteness a little
+    A = ho.adjacency_from_nx(B)
+    Xo, so = ho.hope_dense_lapack(A, 8, 0.05)
+    for algorithm in (1, 2):
+        m = _fresh_hope(d=8, beta=0.05, oversample=19, tol=1e-10, max_iters=200, compute_residual=1, algorithm=algorithm)
+        X = m.learn_embedding(graph=B)
+        assert np.allclose(m._sigma, so, rtol=SIG_RTOL), (algorithm, m._sigma, so)
+        assert ho.recon_rel_err(X, Xo) < RECON_TOL
+        assert m.stats['resid_max'] < 1e-4
 
 
 def test_divergent_beta_fails_loudly(gpu_ctx):
@@ -92,15 +121,17 @@ def test_divergent_beta_fails_loudly(gpu_ctx):
         m.learn_embedding(graph=G)
 
 
-def test_large_sparse_input_properties(gpu_ctx, hope_oracle):
+@pytest.mark.parametrize('algorithm', [1, 2])
+def test_large_sparse_input_properties(gpu_ctx, hope_oracle, algorithm):
     """SBM at 100k nodes through the CSR entry of the plugin; checked with size-independent properties:
     ascending sigma, orthonormal U and V, SVD residuals of the fp64 matrix-free operator, and sigma
     against the CPU sparse oracle (scipy svds on the same Katz operator)."""
     from gem_b200 import synth
     ho = hope_oracle
     csr = synth.sbm(n=100_000, block=1000, seed=11)
-    m = _fresh_hope(d=16, beta=0.01, tol=1e-8, max_iters=100, min_iters=4, compute_residual=1)
+    m = _fresh_hope(d=16, beta=0.01, tol=1e-8, max_iters=100, min_iters=4, compute_residual=1, algorithm=algorithm)
     X = m.learn_embedding(graph=csr)
+    assert m.stats['algorithm'] == algorithm
     sig = np.asarray(m._sigma, dtype=np.float64)
     assert np.all(np.diff(sig) >= 0)
     A = csr.to_scipy()
