@@ -18,6 +18,7 @@ void count_launch(int k = 1);   // every kernel launch of this library is counte
         if (_e != cudaSuccess) {                                                              \
             gemb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,              \
                             cudaGetErrorString(_e));                                          \
+            (void)cudaGetLastError(); /* clear a non-sticky error for later calls */          \
             return GEMB_ERR_CUDA;                                                             \
         }                                                                                     \
     } while (0)

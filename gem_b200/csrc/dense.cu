@@ -302,7 +302,7 @@ int chol_inverse_launch(gemb_ctx *ctx, int b, double *G, float *Minv, int *rank_
     if (big <= 220 * 1024) {
         static bool attr_set = false;
         if (!attr_set) {
-            GEMB_CUDA(cudaFuncSetAttribute(chol_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+            GEMB_CUDA(cudaFuncSetAttribute(chol_inverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));  // + 4 B static
             attr_set = true;
         }
         chol_inverse_kernel<true><<<1, 1024, big, ctx->stream>>>(b, G, Minv, Minv64, rank_out_dev);
@@ -432,11 +432,11 @@ int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Z
         attr_set = true;
     }
     if (base + 2 * one <= cap)
-        eigh_jacobi_kernel<2><<<1, 1024, base + 2 * one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-13);
+        eigh_jacobi_kernel<2><<<1, 1024, base + 2 * one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-11);
     else if (base + one <= cap)
-        eigh_jacobi_kernel<1><<<1, 1024, base + one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-13);
+        eigh_jacobi_kernel<1><<<1, 1024, base + one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-11);
     else
-        eigh_jacobi_kernel<0><<<1, 1024, base, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-13);
+        eigh_jacobi_kernel<0><<<1, 1024, base, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-11);
     GEMB_CUDA(cudaGetLastError());
     count_launch();
     return GEMB_OK;

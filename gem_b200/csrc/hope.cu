@@ -219,6 +219,55 @@ static int axpby_launch(HopeWork &W, float a, const float *P, float c, const flo
     return GEMB_OK;
 }
 
+// out[0] = max_i sum_j |a_ij| (= ||A||_inf), out[1] = max(0, -min_ij a_ij)  (0 <=> all weights >= 0)
+__global__ void csr_rowsum_kernel(int64_t n, const int32_t *__restrict__ indptr, const float *__restrict__ vals,
+                                  double *__restrict__ out) {
+    double mx = 0.0, neg = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+        const int s = indptr[r], e = indptr[r + 1];
+        double acc = 0.0;
+        if (vals) {
+            for (int i = s; i < e; i++) { const double v = vals[i]; acc += fabs(v); if (-v > neg) neg = -v; }
+        } else acc = (double)(e - s);
+        if (acc > mx) mx = acc;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        neg = fmax(neg, __shfl_xor_sync(0xffffffffu, neg, o));
+    }
+    if ((threadIdx.x & 31) == 0) {   // non-negative doubles order like their bit patterns
+        atomicMax((unsigned long long *)out, (unsigned long long)__double_as_longlong(mx));
+        atomicMax((unsigned long long *)(out + 1), (unsigned long long)__double_as_longlong(neg));
+    }
+}
+
+static int comm_allreduce_max_f64(HopeWork &W, double *buf, size_t count) {
+    if (W.c->nranks == 1) return GEMB_OK;
+    NcclApi *api = nccl_api();
+    if (!api) return GEMB_ERR_NCCL;
+    ncclResult_t r = api->AllReduce(buf, buf, count, ncclDouble, ncclMax, (ncclComm_t)W.c->comm, W.c->stream);
+    if (r != ncclSuccess) { set_error("ncclAllReduce(max): %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
+    return GEMB_OK;
+}
+
+// ||A||_inf and the sign of the weights in one pass over the CSR shard
+static int rowsum_bound(HopeWork &W, double *norm_inf, bool *nonneg) {
+    gemb_ctx *c = W.c;
+    GEMB_CUDA(cudaMemsetAsync(W.scal, 0, 2 * sizeof(double), c->stream));
+    if (W.rows > 0) {
+        csr_rowsum_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(W.rows, W.g->A.indptr, W.g->A.data, W.scal);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    GEMB_TRY(comm_allreduce_max_f64(W, W.scal, 2));
+    double h[2];
+    GEMB_CUDA(cudaMemcpyAsync(h, W.scal, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    GEMB_CUDA(cudaStreamSynchronize(c->stream));
+    *norm_inf = h[0];
+    *nonneg = (h[1] == 0.0);
+    return GEMB_OK;
+}
+
 // ||A||_2 by power iteration on A^T A with a 4-column block
 static int estimate_norm2(HopeWork &W, uint64_t seed, float *x, float *y, float *z, double *out) {
     gemb_ctx *c = W.c;
@@ -389,18 +438,25 @@ static int orth_rotated(HopeWork &W, const float *F, float *tmp, float *dst) {
 // ------------------------------------------------------------------------------------ symmetric solver
 static inline double katz_f(double beta, double l) { return beta * l / (1.0 - beta * l); }
 
-static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double nrm, HopeResult &R) {
+// nrm: tight estimate of ||A||_2 (power iteration), or < 0 when A is symmetric with non-negative weights: then
+// lambda_max = rho(A) >= |lambda_min| (Perron-Frobenius), so 1.05 * (largest Ritz value) bounds the spectrum on
+// both sides and the 2 x 16 narrow SpMM sweeps of the power iteration are not needed; hard_bound = ||A||_inf.
+static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double nrm, double hard_bound, HopeResult &R) {
     gemb_ctx *c = W.c;
     const int b = W.b, k = d / 2;
     R.algorithm = 2;
     R.katz_terms = 0;
     float *V = W.buf[0], *AV = W.buf[1];
     float *pool[3] = {W.buf[2], W.buf[3], W.buf[4]};
-    const double bound = nrm * 1.02 + 1e-30;
+    const bool ritz_bound = nrm < 0.0;
+    double bound = ritz_bound ? hard_bound * 1.02 + 1e-30 : nrm * 1.02 + 1e-30;
 
     GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)W.g->row0, pool[0]));
     GEMB_TRY(cholqr2(W, pool[0], pool[1], V));
-    const int warm = 3;   // plain power steps V <- orth(A V) before the first Chebyshev filter
+    for (int s = 0; s < 3; s++) {   // warm-up: plain power steps V <- orth(A V) (no Rayleigh-Ritz needed yet)
+        GEMB_TRY(dist_spmm(W, false, b, 1.f, V, nullptr, AV, true));
+        GEMB_TRY(cholqr2(W, AV, pool[0], V));
+    }
 
     std::vector<double> lam(b), gval(b), th_sorted(b), th_prev(b, 0.0);
     std::vector<int> order(b);
@@ -417,6 +473,11 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         GEMB_TRY(c->t_dense.end(c->stream));
         GEMB_CUDA(cudaMemcpyAsync(lam.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
         GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        if (ritz_bound) {
+            double amax = 0.0;
+            for (int i = 0; i < b; i++) amax = std::max(amax, fabs(lam[i]));
+            bound = std::min(hard_bound * 1.02, 1.05 * amax) + 1e-30;
+        }
         for (int i = 0; i < b; i++) {
             const double l = std::max(-bound, std::min(bound, lam[i]));  // Ritz values lie inside the spectrum
             gval[i] = fabs(katz_f(beta, l));
@@ -435,10 +496,6 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         if (it >= o.min_iters && change <= (double)o.tol) { R.converged = 1; break; }
         if (it == o.max_iters) break;
 
-        if (it <= warm) {                                              // A V is already there: one power step
-            GEMB_TRY(orth_rotated(W, AV, pool[0], V));
-            continue;
-        }
         // damped set {l : |f(l)| < tau}, tau = smallest |f| in the block
         const double tau = gval[order[b - 1]];
         double hi = tau / ((double)beta * (1.0 + tau));
@@ -448,13 +505,23 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         if (hi - lo < 2e-3 * bound) { const double mid = 0.5 * (hi + lo); lo = mid - 1e-3 * bound; hi = mid + 1e-3 * bound; }
         const double e = 0.5 * (hi - lo), c0 = 0.5 * (hi + lo);
         const double aL = lam[order[0]] >= c0 ? bound : -bound;       // normalise p(aL) = 1 at the dominant end
+        // fp32 guard: the filter spreads the block's columns over a dynamic range T_m(x_L) ~ g^m / 2; the
+        // Gram-based orthonormalisation squares it, so keep it below ~2^8 (degree m), else take a power step
+        const double xL = fabs(aL - c0) / e;
+        const double growth = xL + sqrt(std::max(xL * xL - 1.0, 0.0));
+        int deg = o.cheb_degree;
+        if (growth > 1.0 + 1e-9) deg = std::min(deg, (int)floor(log(2.0 * 256.0) / log(growth)));
+        if (deg < 2) {                                                 // A V is already there: one power step
+            GEMB_TRY(orth_rotated(W, AV, pool[0], V));
+            continue;
+        }
         double sigma = e / (aL - c0);
         const double tau2 = 2.0 / sigma;
         // Y1 = (sigma/e) (A V - c0 V)  -- A V is the Rayleigh-Ritz product, no extra SpMM
         float *prev = V, *cur = pool[0];
         float *free_a = pool[1], *free_b = pool[2];
         GEMB_TRY(axpby_launch(W, (float)(sigma / e), AV, (float)(-sigma * c0 / e), V, cur));
-        for (int i = 2; i <= o.cheb_degree; i++) {
+        for (int i = 2; i <= deg; i++) {
             const double sn = 1.0 / (tau2 - sigma);
             float *nxt = free_a;
             GEMB_TRY(dist_spmm3(W, false, b, (float)(2.0 * sn / e), cur, (float)(-2.0 * sn * c0 / e), true,
@@ -510,7 +577,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
 
     if (o.compute_residual) {
         // check the triplets against the Katz operator itself: || S^T u - sigma v || / sigma_max
-        const int J = katz_terms_for(beta, nrm, o.katz_tol);
+        const int J = katz_terms_for(beta, ritz_bound ? bound / 1.02 : nrm, o.katz_tol);
         std::vector<float> MP((size_t)b * b, 0.f), MQ((size_t)b * b, 0.f);
         for (int col = 0; col < b; col++) {
             const double l = std::max(-bound, std::min(bound, lam[col]));
@@ -606,9 +673,16 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     GEMB_CUDA(cudaEventCreate(&ev1));
     GEMB_CUDA(cudaEventRecord(ev0, c->stream));
 
-    double nrm = 0.0;
+    double nrm = 0.0, hard_bound = 0.0;
     int J = o.katz_terms;
-    if (J <= 0 || algo == 2) {
+    bool need_power = (J <= 0 && algo == 1);
+    if (algo == 2) {
+        bool nonneg = false;
+        GEMB_TRY(rowsum_bound(W, &hard_bound, &nonneg));
+        if (nonneg && (double)beta * hard_bound * 1.02 < 1.0) nrm = -1.0;   // spectrum bounds from Ritz values
+        else need_power = true;
+    }
+    if (need_power) {
         GEMB_TRY(estimate_norm2(W, o.seed, W.buf[3], W.buf[4], W.buf[2], &nrm));
         if ((double)beta * nrm * 1.02 >= 1.0) {
             set_error("beta * ||A||_2 = %.4g >= 1: the Katz series (I - beta A)^-1 beta A does not converge; "
@@ -617,11 +691,12 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
             return GEMB_ERR_DIVERGE;
         }
         if (J <= 0) J = katz_terms_for(beta, nrm, o.katz_tol);
+        if (hard_bound <= 0.0) hard_bound = nrm;
         for (int i = 2; i < 5; i++) GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));  // width-4 scratch
     }
 
     HopeResult R;
-    int s = (algo == 2) ? hope_symmetric(W, o, d, beta, nrm, R) : hope_general(W, o, d, beta, J, R);
+    int s = (algo == 2) ? hope_symmetric(W, o, d, beta, nrm, hard_bound, R) : hope_general(W, o, d, beta, J, R);
     if (s != GEMB_OK) { cudaFree(R.Xalloc); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return s; }
 
     GEMB_CUDA(cudaEventRecord(ev1, c->stream));
@@ -660,7 +735,7 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         stats->total_ms = total_ms;
         stats->h2d_ms = 0.0;
         stats->d2h_ms = d2h_ms;
-        stats->norm2_A = (float)nrm;
+        stats->norm2_A = (float)(nrm >= 0.0 ? nrm : hard_bound);   /* ||A||_inf when no power iteration ran */
         stats->ritz_change = (float)R.change;
         stats->resid_max = R.resid_max;
     }

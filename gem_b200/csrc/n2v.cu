@@ -151,9 +151,10 @@ struct SgnsParams {
     int64_t n_walks_total;    // all walks of an epoch (all ranks)
     int walk_len, d, win, iters, epoch;
     float *syn_pos, *syn_neg; // rows by node id
-    const int32_t *KT;        // V  (token space)
-    const double *UT;         // V
+    const int32_t *KT;        // V  (token space): first-level lookup of RndUnigramInt
+    const double *UT;         // V  (kept for reference / debugging)
     const int32_t *tok2node;  // V
+    const uint4 *ent;         // V: {thr, node(X), node(KT[X]), 0}: Y < UT[X]  <=>  draw < thr   (exact, see host)
     int64_t V;
     uint32_t seed;            // training TRnd seed
     uint64_t seq_start;       // sequential mode: stream position where training starts (= V*d)
@@ -210,8 +211,79 @@ __device__ __forceinline__ float sg_grad(float f, int label, float alpha) {
     if (f > SG_MAXEXP) return (float)(label - 1) * alpha;
     if (f < -SG_MAXEXP) return (float)label * alpha;
     const float fq = truncf(f * 10000.f) * 1e-4f;
-    const float e = expf(fq);
-    return ((float)(label - 1) + 1.f / (1.f + e)) * alpha;
+    const float e = __expf(fq);
+    return ((float)(label - 1) + __fdividef(1.f, 1.f + e)) * alpha;
+}
+
+__device__ __forceinline__ uint32_t mulmod_fold(uint32_t a, uint32_t b) {
+    const uint64_t p = (uint64_t)a * (uint64_t)b;            // < 2^62
+    uint64_t r = (p & RNG_M) + (p >> 31);                    // < 2^32
+    r = (r & RNG_M) + (r >> 31);
+    return (uint32_t)(r >= RNG_M ? r - RNG_M : r);
+}
+
+// one (centre = word, context = ctx) pair: 1 positive + 5 negatives.  `seqpath` processes the negatives one
+// after the other through memory (needed when a negative row repeats inside the group).
+template <int NV, bool VEC>
+__device__ __forceinline__ void sgns_pair(const SgnsParams &P, int lane, int d, int ctx, const int (&tgt)[SG_NEG],
+                                          bool seqpath, float alpha, float (&snw)[NV]) {
+    float sp[NV], neu[NV];
+    float *sp_row = P.syn_pos + (int64_t)ctx * d;
+    RowIO<NV, VEC>::load(sp_row, d, lane, sp);
+    if (!seqpath) {
+        float sn[SG_NEG][NV];
+#pragma unroll
+        for (int j = 0; j < SG_NEG; j++)
+            if (tgt[j] >= 0) RowIO<NV, VEC>::load(P.syn_neg + (int64_t)tgt[j] * d, d, lane, sn[j]);
+        {
+            float f = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; v++) f = fmaf(sp[v], snw[v], f);
+            f = warp_sum(f);
+            const float g = sg_grad(f, 1, alpha);
+#pragma unroll
+            for (int v = 0; v < NV; v++) { neu[v] = g * snw[v]; snw[v] = fmaf(g, sp[v], snw[v]); }
+        }
+#pragma unroll
+        for (int j = 0; j < SG_NEG; j++) {
+            if (tgt[j] < 0) continue;
+            float f = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; v++) f = fmaf(sp[v], sn[j][v], f);
+            f = warp_sum(f);
+            const float g = sg_grad(f, 0, alpha);
+#pragma unroll
+            for (int v = 0; v < NV; v++) { neu[v] = fmaf(g, sn[j][v], neu[v]); sn[j][v] = fmaf(g, sp[v], sn[j][v]); }
+            RowIO<NV, VEC>::store(P.syn_neg + (int64_t)tgt[j] * d, d, lane, sn[j]);
+        }
+    } else {
+        {
+            float f = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; v++) f = fmaf(sp[v], snw[v], f);
+            f = warp_sum(f);
+            const float g = sg_grad(f, 1, alpha);
+#pragma unroll
+            for (int v = 0; v < NV; v++) { neu[v] = g * snw[v]; snw[v] = fmaf(g, sp[v], snw[v]); }
+        }
+        for (int j = 0; j < SG_NEG; j++) {
+            if (tgt[j] < 0) continue;
+            float sn[NV];
+            float *row = P.syn_neg + (int64_t)tgt[j] * d;
+            RowIO<NV, VEC>::load(row, d, lane, sn);
+            float f = 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; v++) f = fmaf(sp[v], sn[v], f);
+            f = warp_sum(f);
+            const float g = sg_grad(f, 0, alpha);
+#pragma unroll
+            for (int v = 0; v < NV; v++) { neu[v] = fmaf(g, sn[v], neu[v]); sn[v] = fmaf(g, sp[v], sn[v]); }
+            RowIO<NV, VEC>::store(row, d, lane, sn);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; v++) sp[v] += neu[v];
+    RowIO<NV, VEC>::store(sp_row, d, lane, sp);
 }
 
 template <int NV, bool VEC>
@@ -229,6 +301,11 @@ sgns_kernel(SgnsParams P) {
     const double denom = (double)((int64_t)P.iters * all_words + 1);
     // upper bound of draws per walk in parallel mode: per word 1 + (2*win) * SG_NEG * 2
     const uint64_t stride = (uint64_t)L * (uint64_t)(1 + 2 * win * SG_NEG * 2);
+    const uint32_t Vu = (uint32_t)P.V;
+    // lane j < 5 draws negative j: its two TRnd values are draws 2j+1 and 2j+2 after the current state
+    const uint32_t a_first = lane == 0 ? 16807u : lane == 1 ? lcg_skip(1u, 3) : lane == 2 ? lcg_skip(1u, 5)
+                             : lane == 3 ? lcg_skip(1u, 7) : lcg_skip(1u, 9);
+    const uint32_t a_ten = lcg_skip(1u, 10);
     uint32_t st = 0;
     if (P.sequential) st = *P.seq_state;
     unsigned long long pairs = 0;
@@ -256,61 +333,24 @@ sgns_kernel(SgnsParams P) {
                 const int c = pos - win + a;
                 if (c < 0 || c >= L) continue;
                 const int ctx = wk[c];
-                // negatives: draws first (they do not depend on data), then the row loads together
+                // ---- 5 negatives drawn by lanes 0..4 in parallel (RndUnigramInt: first lookup through KTable)
+                int mine = -2 - lane;                                   // unique dummy: never matches
+                if (lane < SG_NEG) {
+                    const uint32_t s1 = mulmod_fold(st, a_first);
+                    const uint32_t s2 = mulmod_fold(s1, 16807u);
+                    const uint32_t i0 = (uint32_t)(((uint64_t)s1 * (uint64_t)Vu) / (uint64_t)RNG_M);
+                    const int X = P.KT[i0];
+                    const uint4 e = P.ent[X];
+                    const int node = s2 < e.x ? (int)e.y : (int)e.z;
+                    if (node != word) mine = node;                      // `if (Target == Word) continue;`
+                }
+                st = mulmod_fold(st, a_ten);
                 int tgt[SG_NEG];
 #pragma unroll
-                for (int j = 0; j < SG_NEG; j++) {
-                    st = lcg_next(st);
-                    const int X = P.KT[(int64_t)__dmul_rn(lcg_uni(st), (double)P.V)];   // RndUnigramInt: through KTable
-                    st = lcg_next(st);
-                    const double Y = lcg_uni(st);
-                    const int tok = Y < P.UT[X] ? X : P.KT[X];
-                    const int node = P.tok2node[tok];
-                    tgt[j] = node == word ? -1 : node;   // `if (Target == Word) continue;`
-                }
-                float sp[NV], neu[NV], sn[SG_NEG][NV];
-                float *sp_row = P.syn_pos + (int64_t)ctx * d;
-                RowIO<NV, VEC>::load(sp_row, d, lane, sp);
-#pragma unroll
-                for (int j = 0; j < SG_NEG; j++)
-                    if (tgt[j] >= 0) RowIO<NV, VEC>::load(P.syn_neg + (int64_t)tgt[j] * d, d, lane, sn[j]);
-                // positive target (label 1), row cached in registers for the whole window
-                {
-                    float f = 0.f;
-#pragma unroll
-                    for (int v = 0; v < NV; v++) f = fmaf(sp[v], snw[v], f);
-                    f = warp_sum(f);
-                    const float g = sg_grad(f, 1, alpha);
-#pragma unroll
-                    for (int v = 0; v < NV; v++) { neu[v] = g * snw[v]; snw[v] = fmaf(g, sp[v], snw[v]); }
-                }
-#pragma unroll
-                for (int j = 0; j < SG_NEG; j++) {
-                    if (tgt[j] < 0) continue;
-                    float f = 0.f;
-#pragma unroll
-                    for (int v = 0; v < NV; v++) f = fmaf(sp[v], sn[j][v], f);
-                    f = warp_sum(f);
-                    const float g = sg_grad(f, 0, alpha);
-#pragma unroll
-                    for (int v = 0; v < NV; v++) { neu[v] = fmaf(g, sn[j][v], neu[v]); sn[j][v] = fmaf(g, sp[v], sn[j][v]); }
-                    // the same negative drawn again later in this group must see this update
-                    bool again = false;
-#pragma unroll
-                    for (int j2 = j + 1; j2 < SG_NEG; j2++) {
-                        if (j2 > j && tgt[j2] == tgt[j]) {
-                            if (!again) {
-#pragma unroll
-                                for (int v = 0; v < NV; v++) sn[j2][v] = sn[j][v];
-                                again = true;
-                            }
-                        }
-                    }
-                    if (!again) RowIO<NV, VEC>::store(P.syn_neg + (int64_t)tgt[j] * d, d, lane, sn[j]);
-                }
-#pragma unroll
-                for (int v = 0; v < NV; v++) sp[v] += neu[v];
-                RowIO<NV, VEC>::store(sp_row, d, lane, sp);
+                for (int j = 0; j < SG_NEG; j++) tgt[j] = __shfl_sync(0xffffffffu, mine, j);
+                const unsigned same = __match_any_sync(0xffffffffu, mine);
+                const bool dup = __any_sync(0xffffffffu, lane < SG_NEG && mine >= 0 && __popc(same) > 1);
+                sgns_pair<NV, VEC>(P, lane, d, ctx, tgt, dup, alpha, snw);
                 pairs++;
             }
             RowIO<NV, VEC>::store(snw_row, d, lane, snw);
@@ -381,12 +421,13 @@ struct N2VDev {
     int32_t *K = nullptr, *scratch = nullptr, *order = nullptr, *walks = nullptr;
     unsigned long long *first_pos = nullptr, *cnt = nullptr, *pairs = nullptr;
     int32_t *KT = nullptr, *tok2node = nullptr;
+    uint4 *ent = nullptr;
     double *UT = nullptr;
     float *syn_pos = nullptr, *syn_neg = nullptr, *pos0 = nullptr, *delta = nullptr;
     uint32_t *seq_state = nullptr;
     ~N2VDev() {
         cudaFree(w); cudaFree(U); cudaFree(K); cudaFree(scratch); cudaFree(order); cudaFree(walks);
-        cudaFree(first_pos); cudaFree(cnt); cudaFree(pairs); cudaFree(KT); cudaFree(tok2node); cudaFree(UT);
+        cudaFree(first_pos); cudaFree(cnt); cudaFree(pairs); cudaFree(KT); cudaFree(tok2node); cudaFree(UT); cudaFree(ent);
         cudaFree(syn_pos); cudaFree(syn_neg); cudaFree(pos0); cudaFree(delta); cudaFree(seq_state);
     }
 };
@@ -601,6 +642,20 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
     std::vector<int32_t> KT;
     std::vector<double> UT;
     unigram_alias(vocab, KT, UT);
+    // ent[X] = {thr, node(X), node(KT[X])} with thr the smallest draw s for which (double)s / m >= UT[X]:
+    // `Y < UT[X]` of RndUnigramInt (Y = s / m in fp64) is then exactly `s < thr` in integers.
+    std::vector<uint4> ent(V);
+    for (int64_t i = 0; i < V; i++) {
+        const double u = UT[i];
+        int64_t t = (int64_t)ceil(u * 2147483647.0);
+        if (t < 0) t = 0;
+        if (t > 2147483647LL) t = 2147483647LL;
+        while (t > 0 && (double)(t - 1) / 2147483647.0 >= u) t--;
+        while (t < 2147483647LL && (double)t / 2147483647.0 < u) t++;
+        ent[i] = make_uint4((uint32_t)t, (uint32_t)tok2node[i], (uint32_t)tok2node[KT[i]], 0u);
+    }
+    GEMB_CUDA(cudaMalloc(&D.ent, sizeof(uint4) * V));
+    GEMB_CUDA(cudaMemcpyAsync(D.ent, ent.data(), sizeof(uint4) * V, cudaMemcpyHostToDevice, c->stream));
     GEMB_CUDA(cudaMalloc(&D.KT, sizeof(int32_t) * V));
     GEMB_CUDA(cudaMalloc(&D.UT, sizeof(double) * V));
     GEMB_CUDA(cudaMalloc(&D.tok2node, sizeof(int32_t) * V));
@@ -636,7 +691,7 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
     SgnsParams P;
     P.walks = D.walks; P.n_walks_local = n_local; P.walk_offset = w_begin; P.n_walks_total = total_walks;
     P.walk_len = walk_len; P.d = d; P.win = con_size; P.iters = max_iter; P.epoch = 0;
-    P.syn_pos = D.syn_pos; P.syn_neg = D.syn_neg; P.KT = D.KT; P.UT = D.UT; P.tok2node = D.tok2node; P.V = V;
+    P.syn_pos = D.syn_pos; P.syn_neg = D.syn_neg; P.KT = D.KT; P.UT = D.UT; P.tok2node = D.tok2node; P.ent = D.ent; P.V = V;
     P.seed = (uint32_t)seed; P.seq_start = (uint64_t)V * d; P.sequential = sequential ? 1 : 0;
     P.seq_state = D.seq_state; P.pair_counter = D.pairs;
     const int threads = 128;
