@@ -58,9 +58,12 @@ struct gemb_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;      // side stream: single-CTA factorizations overlapped with SpMM sweeps
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // multi-GPU
     int rank = 0, nranks = 1;
     void *comm = nullptr;  // ncclComm_t
+    int *tile_counter = nullptr;  // device work counter of the persistent SpMM kernel
     gemb::Timer t_spmm, t_dense, t_comm, t_misc;
 };
 
@@ -79,6 +82,7 @@ struct gemb_graph {
     int64_t n_shard = 0;  // rows per rank used for collectives (= ceil(n / nranks)); n_local <= n_shard
     int64_t n_pad = 0;    // n_shard * nranks
     bool symmetric = false;
+    bool replicated = false;  // multi-GPU: the whole graph on every rank (node2vec) instead of a row shard
     gemb_csr_dev A, AT;   // AT aliases A when symmetric
 };
 

@@ -116,6 +116,13 @@ int gemb_ctx_create(int device, gemb_ctx **out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     GEMB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        int lo_prio = 0, hi_prio = 0;   // side stream gets the highest priority: its single CTA must not queue behind 83k SpMM CTAs
+        GEMB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        GEMB_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi_prio));
+    }
+    GEMB_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    GEMB_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     *out = c;
     return GEMB_OK;
 }
@@ -131,6 +138,10 @@ int gemb_ctx_destroy(gemb_ctx *c) {
     c->t_dense.destroy();
     c->t_comm.destroy();
     c->t_misc.destroy();
+    cudaFree(c->tile_counter);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return GEMB_OK;
@@ -218,8 +229,10 @@ int gemb_graph_upload(gemb_ctx *c, int64_t n, int64_t row0, int64_t n_local, con
     g->n_shard = (n + c->nranks - 1) / c->nranks;
     g->n_pad = g->n_shard * c->nranks;
     if (c->nranks > 1) {
-        if (row0 != g->n_shard * c->rank || n_local > g->n_shard) {
-            set_error("multi-GPU shard must be rows [rank*ceil(n/P), ...): got row0=%lld n_local=%lld",
+        // either this rank's row shard (HOPE) or the whole graph replicated on every rank (node2vec)
+        g->replicated = (row0 == 0 && n_local == n);
+        if (!g->replicated && (row0 != g->n_shard * c->rank || n_local > g->n_shard)) {
+            set_error("multi-GPU upload must be rows [rank*ceil(n/P), ...) or the whole graph: got row0=%lld n_local=%lld",
                       (long long)row0, (long long)n_local);
             delete g;
             return GEMB_ERR_ARG;

@@ -460,19 +460,58 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
 
     std::vector<double> lam(b), gval(b), th_sorted(b), th_prev(b, 0.0);
     std::vector<int> order(b);
+    struct Plan { bool valid = false; int deg = 0; double e = 0, c0 = 0, sigma1 = 0; } plan;
+
+    // scaled three-term Chebyshev recurrence on [c0 - e, c0 + e], normalised at the dominant end; returns the
+    // filtered block (one of the pool buffers); A V must be current
+    auto run_filter = [&](const Plan &pl, float **out) -> int {
+        double sigma = pl.sigma1;
+        const double e = pl.e, c0 = pl.c0, tau2 = 2.0 / pl.sigma1;
+        float *prev = V, *cur = pool[0];
+        float *free_a = pool[1], *free_b = pool[2];
+        // Y1 = (sigma/e) (A V - c0 V)  -- A V is the Rayleigh-Ritz product, no extra SpMM
+        GEMB_TRY(axpby_launch(W, (float)(sigma / e), AV, (float)(-sigma * c0 / e), V, cur));
+        for (int i = 2; i <= pl.deg; i++) {
+            const double sn = 1.0 / (tau2 - sigma);
+            float *nxt = free_a;
+            GEMB_TRY(dist_spmm3(W, false, b, (float)(2.0 * sn / e), cur, (float)(-2.0 * sn * c0 / e), true,
+                                (float)(-sigma * sn), prev, nxt, true));
+            sigma = sn;
+            // rotate: the old `prev` becomes free unless it is V (V must survive until the new basis exists)
+            float *old_prev = prev;
+            prev = cur;
+            cur = nxt;
+            if (old_prev == V) { free_a = free_b; free_b = nullptr; }
+            else { free_a = old_prev; }
+        }
+        *out = cur;
+        return GEMB_OK;
+    };
+
     for (int it = 1; it <= o.max_iters; it++) {
         R.iters = it;
-        // Rayleigh-Ritz on A
+        // Rayleigh-Ritz on A: T = V^T A V on the main stream, its eigen-decomposition (one CTA) on the side stream
         GEMB_TRY(dist_spmm(W, false, b, 1.f, V, nullptr, AV, true));
         GEMB_TRY(gram_full(W, V, AV, W.G2));
         symmetrize_kernel<<<(b * b + 255) / 256, 256, 0, c->stream>>>(b, W.G2);
         GEMB_CUDA(cudaGetLastError());
         count_launch();
-        GEMB_TRY(c->t_dense.begin(c->stream));
-        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs));
-        GEMB_TRY(c->t_dense.end(c->stream));
-        GEMB_CUDA(cudaMemcpyAsync(lam.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
-        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        GEMB_CUDA(cudaEventRecord(c->ev_a, c->stream));
+        GEMB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_a, 0));
+        {
+            cudaStream_t main_stream = c->stream;
+            c->stream = c->stream2;                                    // eigh_launch uses ctx->stream
+            const int es = eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs);
+            c->stream = main_stream;
+            GEMB_TRY(es);
+        }
+        GEMB_CUDA(cudaMemcpyAsync(lam.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream2));
+        GEMB_CUDA(cudaEventRecord(c->ev_b, c->stream2));
+        // while the Jacobi sweeps run on one SM, start the filter with the interval of the PREVIOUS round
+        // (the damped set only grows from round to round, so the lagged interval is conservative)
+        float *filtered = nullptr;
+        if (plan.valid && plan.deg >= 2 && it < o.max_iters) GEMB_TRY(run_filter(plan, &filtered));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream2));
         if (ritz_bound) {
             double amax = 0.0;
             for (int i = 0; i < b; i++) amax = std::max(amax, fabs(lam[i]));
@@ -503,43 +542,36 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         lo = std::max(lo, -bound);
         hi = std::min(hi, bound);
         if (hi - lo < 2e-3 * bound) { const double mid = 0.5 * (hi + lo); lo = mid - 1e-3 * bound; hi = mid + 1e-3 * bound; }
-        const double e = 0.5 * (hi - lo), c0 = 0.5 * (hi + lo);
-        const double aL = lam[order[0]] >= c0 ? bound : -bound;       // normalise p(aL) = 1 at the dominant end
+        Plan np;
+        np.valid = true;
+        np.e = 0.5 * (hi - lo);
+        np.c0 = 0.5 * (hi + lo);
+        const double aL = lam[order[0]] >= np.c0 ? bound : -bound;    // normalise p(aL) = 1 at the dominant end
+        np.sigma1 = np.e / (aL - np.c0);
         // fp32 guard: the filter spreads the block's columns over a dynamic range T_m(x_L) ~ g^m / 2; the
         // Gram-based orthonormalisation squares it, so keep it below ~2^8 (degree m), else take a power step
-        const double xL = fabs(aL - c0) / e;
+        const double xL = fabs(aL - np.c0) / np.e;
         const double growth = xL + sqrt(std::max(xL * xL - 1.0, 0.0));
-        int deg = o.cheb_degree;
-        if (growth > 1.0 + 1e-9) deg = std::min(deg, (int)floor(log(2.0 * 256.0) / log(growth)));
-        if (deg < 2) {                                                 // A V is already there: one power step
-            GEMB_TRY(orth_rotated(W, AV, pool[0], V));
-            continue;
+        np.deg = o.cheb_degree;
+        if (growth > 1.0 + 1e-9) np.deg = std::min(np.deg, (int)floor(log(2.0 * 256.0) / log(growth)));
+
+        GEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));         // Z is needed from here on
+        if (!filtered) {
+            if (np.deg < 2) {                                          // A V is already there: one power step
+                GEMB_TRY(orth_rotated(W, AV, pool[0], V));
+                plan = np;
+                continue;
+            }
+            GEMB_TRY(run_filter(np, &filtered));
         }
-        double sigma = e / (aL - c0);
-        const double tau2 = 2.0 / sigma;
-        // Y1 = (sigma/e) (A V - c0 V)  -- A V is the Rayleigh-Ritz product, no extra SpMM
-        float *prev = V, *cur = pool[0];
-        float *free_a = pool[1], *free_b = pool[2];
-        GEMB_TRY(axpby_launch(W, (float)(sigma / e), AV, (float)(-sigma * c0 / e), V, cur));
-        for (int i = 2; i <= deg; i++) {
-            const double sn = 1.0 / (tau2 - sigma);
-            float *nxt = free_a;
-            GEMB_TRY(dist_spmm3(W, false, b, (float)(2.0 * sn / e), cur, (float)(-2.0 * sn * c0 / e), true,
-                                (float)(-sigma * sn), prev, nxt, true));
-            sigma = sn;
-            // rotate: the old `prev` becomes free unless it is V (V must survive until the new basis exists)
-            float *old_prev = prev;
-            prev = cur;
-            cur = nxt;
-            if (old_prev == V) { free_a = free_b; free_b = nullptr; }
-            else { free_a = old_prev; }
-        }
-        // orthonormalise the filtered block into V; scratch = any block that is neither cur nor V
+        plan = np;
+        // orthonormalise the filtered block into V; scratch = any block that is neither `filtered` nor V
         float *tmp = nullptr;
         for (float *cand : {pool[0], pool[1], pool[2], AV})
-            if (cand != cur) { tmp = cand; break; }
-        GEMB_TRY(orth_rotated(W, cur, tmp, V));
+            if (cand != filtered) { tmp = cand; break; }
+        GEMB_TRY(orth_rotated(W, filtered, tmp, V));
     }
+    GEMB_CUDA(cudaStreamSynchronize(c->stream));   // a speculative filter of the last round may still be running
 
     // ---- extraction: top k by |f|, ascending sigma
     std::vector<int> sel(order.begin(), order.begin() + k);
@@ -621,6 +653,7 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     GEMB_ARG(!stats || stats->struct_size == sizeof(gemb_hope_stats), "stats.struct_size");
     gemb_ctx *c = g->ctx;
     GEMB_CUDA(cudaSetDevice(c->device));
+    GEMB_ARG(!(c->nranks > 1 && g->replicated), "multi-GPU HOPE needs row shards (upload rows [rank*ceil(n/P), ...))");
     Opts o;
     if (uo) {
         GEMB_ARG(uo->struct_size == sizeof(gemb_hope_opts), "opts.struct_size");

@@ -10,6 +10,7 @@
 // broadcast).  The nonzero loop is unrolled by 4 so that each thread keeps 4 independent 16-byte
 // gathers in flight.  The Horner epilogue (X0 + alpha * acc) is fused: one extra coalesced read.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace gemb {
 
@@ -83,6 +84,83 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
     Y[row * G + c] = r;
 }
 
+// ---- v2: one persistent 1024-thread CTA per SM walks whole row TILES (dynamic tile counter).  All 51 row groups
+// of an SM then gather from the same neighbourhood of X at the same time, so the rows a community shares are
+// served by that SM's L1 instead of L2 (v1 spreads consecutive row groups over all 148 SMs: 17 % L1 hits).
+template <bool HAS_VAL, bool HAS_X0, bool HAS_SELF>
+__global__ void __launch_bounds__(1024, 1)
+spmm_tile_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                 const float *__restrict__ vals, int64_t n_rows, int G, int groups, int tile_rows,
+                 float alpha, float gamma, float delta, const float4 *__restrict__ X,
+                 const float4 *__restrict__ Xself, const float4 *__restrict__ X0,
+                 float4 *__restrict__ Y, int *__restrict__ tile_counter) {
+    __shared__ int s_tile[2];
+    const int tid = threadIdx.x;
+    const int lr = tid / G;
+    const int c = tid - lr * G;
+    const bool active = lr < groups;
+    const float4 *Xc = X + c;
+    for (int it = 0;; it++) {
+        if (tid == 0) s_tile[it & 1] = atomicAdd(tile_counter, 1);
+        __syncthreads();
+        const int64_t r0 = (int64_t)s_tile[it & 1] * tile_rows;
+        if (r0 >= n_rows) break;
+        const int64_t r1 = r0 + tile_rows < n_rows ? r0 + tile_rows : n_rows;
+        if (active) {
+            for (int64_t row = r0 + lr; row < r1; row += groups) {
+                const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                int i = s;
+                for (; i + 4 <= e; i += 4) {
+                    const int c0 = __ldg(indices + i), c1 = __ldg(indices + i + 1);
+                    const int c2 = __ldg(indices + i + 2), c3 = __ldg(indices + i + 3);
+                    float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
+                    if (HAS_VAL) {
+                        v0 = __ldg(vals + i); v1 = __ldg(vals + i + 1);
+                        v2 = __ldg(vals + i + 2); v3 = __ldg(vals + i + 3);
+                    }
+                    const float4 x0 = __ldg(Xc + (int64_t)c0 * G);
+                    const float4 x1 = __ldg(Xc + (int64_t)c1 * G);
+                    const float4 x2 = __ldg(Xc + (int64_t)c2 * G);
+                    const float4 x3 = __ldg(Xc + (int64_t)c3 * G);
+                    fma4(acc, v0, x0); fma4(acc, v1, x1); fma4(acc, v2, x2); fma4(acc, v3, x3);
+                }
+                for (; i < e; i++) {
+                    const int c0 = __ldg(indices + i);
+                    const float v0 = HAS_VAL ? __ldg(vals + i) : 1.f;
+                    fma4(acc, v0, __ldg(Xc + (int64_t)c0 * G));
+                }
+                float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+                if (HAS_SELF) {
+                    const float4 z = __ldg(Xself + row * G + c);
+                    r.x = fmaf(gamma, z.x, r.x); r.y = fmaf(gamma, z.y, r.y);
+                    r.z = fmaf(gamma, z.z, r.z); r.w = fmaf(gamma, z.w, r.w);
+                }
+                if (HAS_X0) {
+                    const float4 z = __ldg(X0 + row * G + c);
+                    r.x = fmaf(delta, z.x, r.x); r.y = fmaf(delta, z.y, r.y);
+                    r.z = fmaf(delta, z.z, r.z); r.w = fmaf(delta, z.w, r.w);
+                }
+                Y[row * G + c] = r;
+            }
+        }
+    }
+}
+
+// Measured on B200 (SBM 1M / 20M, b = 80): v2 is SLOWER than v1 (0.73-0.84 ms vs 0.56 ms per sweep for tiles of
+// 256-2048 rows): halving the resident threads costs more than the L1 hits buy.  v1 stays the default;
+// GEMB_SPMM=v2 selects this kernel for experiments, GEMB_SPMM_TILE=<rows> sets its tile.
+static int spmm_variant() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("GEMB_SPMM"); v = (e && e[0] == 'v' && e[1] == '2') ? 2 : 1; }
+    return v;
+}
+static int spmm_tile_rows() {
+    static int t = -1;
+    if (t < 0) { const char *e = getenv("GEMB_SPMM_TILE"); t = e ? atoi(e) : 512; if (t < 64) t = 64; }
+    return t;
+}
+
 int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha,
                 const float *X, const float *X0, float *Y) {
     return spmm3_launch(ctx, A, n_rows, b, alpha, X, 0.f, nullptr, 1.f, X0, Y);
@@ -93,6 +171,34 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
     GEMB_ARG(b > 0 && b % 4 == 0 && b <= 1024, "block width must be a multiple of 4, <= 1024");
     if (n_rows == 0) return GEMB_OK;
     const int G = b / 4;
+    if (spmm_variant() == 2 && n_rows >= 65536 && G <= 256) {
+        if (!ctx->tile_counter) GEMB_CUDA(cudaMalloc(&ctx->tile_counter, sizeof(int)));
+        GEMB_CUDA(cudaMemsetAsync(ctx->tile_counter, 0, sizeof(int), ctx->stream));
+        const int groups = 1024 / G, tile_rows = spmm_tile_rows();
+        const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
+        const int grid2 = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+        const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0, *XS4 = (const float4 *)Xself;
+        float4 *Y4 = (float4 *)Y;
+#define LAUNCH2(V, Z, S)                                                                                   \
+        spmm_tile_kernel<V, Z, S><<<grid2, 1024, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G, groups, \
+                                                                  tile_rows, alpha, gamma, delta, X4, XS4, X04, Y4, \
+                                                                  ctx->tile_counter)
+        const int sel2 = (A.data ? 4 : 0) | (X0 ? 2 : 0) | (Xself ? 1 : 0);
+        switch (sel2) {
+            case 0: LAUNCH2(false, false, false); break;
+            case 1: LAUNCH2(false, false, true); break;
+            case 2: LAUNCH2(false, true, false); break;
+            case 3: LAUNCH2(false, true, true); break;
+            case 4: LAUNCH2(true, false, false); break;
+            case 5: LAUNCH2(true, false, true); break;
+            case 6: LAUNCH2(true, true, false); break;
+            default: LAUNCH2(true, true, true); break;
+        }
+#undef LAUNCH2
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+        return GEMB_OK;
+    }
     const int rows_per_cta = 256 / G;
     const int64_t grid = (n_rows + rows_per_cta - 1) / rows_per_cta;
     GEMB_ARG(grid < (int64_t)2147483647, "grid too large");

@@ -66,8 +66,9 @@ int gemb_comm_init(gemb_ctx *ctx, int rank, int nranks, const void *id);
  * The shard holds rows [row0, row0+n_local) of the n x n adjacency A in CSR form with GLOBAL
  * column ids, and the same row range of A^T (pass indptr_t == NULL when A is symmetric: A^T = A).
  * data / data_t may be NULL (all weights 1.0).  Single GPU: row0 = 0, n_local = n.
- * Multi GPU (after gemb_comm_init): every rank must use n_local = ceil(n / nranks) rows
- * (the last rank may own fewer real rows; pass what it has, the library pads).  */
+ * Multi GPU (after gemb_comm_init): for HOPE every rank uploads rows [rank*ceil(n/P), ...) (the last rank
+ * may own fewer real rows; the library pads); for node2vec every rank uploads the whole graph
+ * (row0 = 0, n_local = n: CSR and alias tables are replicated, the walk index space is sharded).  */
 int gemb_graph_upload(gemb_ctx *ctx, int64_t n, int64_t row0, int64_t n_local,
                       const int32_t *indptr, const int32_t *indices, const float *data,
                       const int32_t *indptr_t, const int32_t *indices_t, const float *data_t,
