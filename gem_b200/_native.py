@@ -17,7 +17,7 @@ UNIQUE_ID_BYTES = 128
 EXPORTS = [
     'gemb_version', 'gemb_last_error', 'gemb_device_count', 'gemb_launch_count', 'gemb_ctx_create', 'gemb_ctx_destroy',
     'gemb_host_alloc', 'gemb_host_free', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
-    'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_hope', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
+    'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_apply', 'gemb_hope', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
 ]
 
 
@@ -77,6 +77,7 @@ def lib():
     L.gemb_graph_free.argtypes = [vp]
     L.gemb_spmm.argtypes = [vp, ctypes.c_int, ctypes.c_int, f32, vp, vp, vp]
     L.gemb_gram.argtypes = [vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
+    L.gemb_apply.argtypes = [vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
     L.gemb_hope.argtypes = [vp, ctypes.c_int, f32, ctypes.POINTER(HopeOpts), vp, vp, ctypes.POINTER(HopeStats)]
     L.gemb_n2v_alias.argtypes = [vp, vp, vp, vp]
     L.gemb_n2v_walks.argtypes = [vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, f64, f64, i32, i64, i64, vp,
@@ -150,6 +151,14 @@ class Context:
         G = np.empty((b1, b2), dtype=np.float64)
         check(lib().gemb_gram(self._h, P.shape[0], _ptr(P), b1, _ptr(Qc), b2, int(bool(tensor_cores)), _ptr(G)))
         return G
+
+    def apply(self, Q, M, tensor_cores=True):
+        """Out = Q @ M through the device kernels (test hook)."""
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        M = np.ascontiguousarray(M, dtype=np.float32)
+        out = np.empty((Q.shape[0], M.shape[1]), dtype=np.float32)
+        check(lib().gemb_apply(self._h, Q.shape[0], _ptr(Q), Q.shape[1], _ptr(M), M.shape[1], int(bool(tensor_cores)), _ptr(out)))
+        return out
 
     def close(self):
         if self._h:

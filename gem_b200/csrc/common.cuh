@@ -103,6 +103,8 @@ int gram_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q
 // Out[n x b2] = Q[n x b1] * M[b1 x b2]  (M fp32 device, row-major, ld = ldm). Out may not alias Q.
 int apply_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *M, int ldm, int b2,
                  float *Out, int ldo);
+int apply_fp32_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *M, int ldm, int b2,
+                      float *Out, int ldo);
 // Small b x b factorizations, single CTA, fp64 (device pointers):
 //  chol_inverse: G (b x b, SPD up to rank deficiency) -> Minv fp32 (b x b) with G = R^T R, Minv = R^-1
 //  (columns whose pivot falls below eps*max are zeroed: Q*Minv then has zero columns there).
@@ -113,7 +115,8 @@ int small_gemm_launch(gemb_ctx *ctx, int b, const double *A, int transA, const d
 int gram_fp32_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G);
 int gram_tc_launch(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, double *G);
 //  eigh: G -> eigenvalues w ascending (b), eigenvectors Z (b x b, column j <-> w[j]); G destroyed.
-int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Zscratch /* b x b */);
+// rel_tol: stop the Jacobi sweeps when ||offdiag||_F <= rel_tol * ||G||_F
+int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Zscratch /* b x b */, double rel_tol = 1e-11);
 int randn_launch(gemb_ctx *ctx, int64_t n, int b, uint64_t seed, uint64_t row_offset, float *X);
 // sum of squares of all entries (fp64 accumulate) -> out_dev[0]
 int sumsq_launch(gemb_ctx *ctx, int64_t count, const float *X, double *out_dev);

@@ -184,9 +184,29 @@ apply_kernel(int64_t n, const float *__restrict__ Q, int b1, const float *__rest
     }
 }
 
+int apply_tc_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *M, int ldm, int b2, float *Out, int ldo);
+
+static int apply_mode() {   // GEMB_APPLY=fp32 forces the CUDA-core kernel; default = tcgen05 where the shape fits
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("GEMB_APPLY");
+        mode = (e && (e[0] == 'f' || e[0] == '0')) ? 0 : 1;
+    }
+    return mode;
+}
+
 int apply_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *M, int ldm, int b2,
                  float *Out, int ldo) {
     if (n == 0 || b2 == 0) return GEMB_OK;
+    if (apply_mode() == 1 && n >= 4096) {
+        const int s = apply_tc_launch(ctx, n, Q, b1, M, ldm, b2, Out, ldo);
+        if (s != GEMB_ERR_UNSUPPORTED) return s;
+    }
+    return apply_fp32_launch(ctx, n, Q, b1, M, ldm, b2, Out, ldo);
+}
+
+int apply_fp32_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *M, int ldm, int b2,
+                      float *Out, int ldo) {
     const int TN = pick_tm(b2);
     const int BN = 16 * TN;
     dim3 grid((unsigned)((n + 63) / 64), (b2 + BN - 1) / BN), block(256);
@@ -420,7 +440,7 @@ eigh_jacobi_kernel(int b, double *__restrict__ Ag, double *__restrict__ w, doubl
     }
 }
 
-int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Zscratch) {
+int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Zscratch, double rel_tol) {
     const int half = ((b + 1) & ~1) / 2;
     const size_t base = sizeof(double) * (3 * half + 2);
     const size_t one = sizeof(double) * (size_t)b * b;
@@ -432,11 +452,11 @@ int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Z
         attr_set = true;
     }
     if (base + 2 * one <= cap)
-        eigh_jacobi_kernel<2><<<1, 1024, base + 2 * one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-11);
+        eigh_jacobi_kernel<2><<<1, 1024, base + 2 * one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, rel_tol);
     else if (base + one <= cap)
-        eigh_jacobi_kernel<1><<<1, 1024, base + one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-11);
+        eigh_jacobi_kernel<1><<<1, 1024, base + one, ctx->stream>>>(b, G, w, Z, Zscratch, 30, rel_tol);
     else
-        eigh_jacobi_kernel<0><<<1, 1024, base, ctx->stream>>>(b, G, w, Z, Zscratch, 30, 1e-11);
+        eigh_jacobi_kernel<0><<<1, 1024, base, ctx->stream>>>(b, G, w, Z, Zscratch, 30, rel_tol);
     GEMB_CUDA(cudaGetLastError());
     count_launch();
     return GEMB_OK;
@@ -557,5 +577,28 @@ extern "C" int gemb_gram(gemb_ctx *c, int64_t n, const float *P, int b1, const f
         if (e != cudaSuccess) { set_error("gemb_gram: %s", cudaGetErrorString(e)); s = GEMB_ERR_CUDA; }
     }
     cudaFree(dP); cudaFree(dQ); cudaFree(dG);
+    return s;
+}
+
+extern "C" int gemb_apply(gemb_ctx *c, int64_t n, const float *Q, int b1, const float *M, int b2,
+                          int use_tensor_cores, float *Out) {
+    using namespace gemb;
+    GEMB_ARG(c && Q && M && Out && n >= 0 && b1 > 0 && b2 > 0, "ctx/Q/M/Out/n/b");
+    GEMB_CUDA(cudaSetDevice(c->device));
+    float *dQ = nullptr, *dM = nullptr, *dO = nullptr;
+    GEMB_CUDA(cudaMalloc(&dQ, sizeof(float) * (size_t)std::max<int64_t>(n, 1) * b1));
+    GEMB_CUDA(cudaMalloc(&dM, sizeof(float) * (size_t)b1 * b2));
+    GEMB_CUDA(cudaMalloc(&dO, sizeof(float) * (size_t)std::max<int64_t>(n, 1) * b2));
+    GEMB_CUDA(cudaMemcpyAsync(dQ, Q, sizeof(float) * (size_t)n * b1, cudaMemcpyHostToDevice, c->stream));
+    GEMB_CUDA(cudaMemcpyAsync(dM, M, sizeof(float) * (size_t)b1 * b2, cudaMemcpyHostToDevice, c->stream));
+    int s = use_tensor_cores ? apply_tc_launch(c, n, dQ, b1, dM, b2, b2, dO, b2)
+                             : apply_fp32_launch(c, n, dQ, b1, dM, b2, b2, dO, b2);
+    if (s == GEMB_ERR_UNSUPPORTED) set_error("gemb_apply: shape (n=%lld, b1=%d, b2=%d) not supported by the tcgen05 kernel", (long long)n, b1, b2);
+    if (s == GEMB_OK) {
+        cudaError_t e = cudaMemcpyAsync(Out, dO, sizeof(float) * (size_t)n * b2, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { set_error("gemb_apply: %s", cudaGetErrorString(e)); s = GEMB_ERR_CUDA; }
+    }
+    cudaFree(dQ); cudaFree(dM); cudaFree(dO);
     return s;
 }

@@ -347,7 +347,7 @@ static int hope_general(HopeWork &W, const Opts &o, int d, float beta, int J, Ho
         GEMB_TRY(gram_full(W, U, U, W.G));                            // T = U^T U
         GEMB_CUDA(cudaMemcpyAsync(W.G2, W.G, sizeof(double) * b * b, cudaMemcpyDeviceToDevice, c->stream));
         GEMB_TRY(c->t_dense.begin(c->stream));
-        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs));
+        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs, std::min(1e-7, std::max(1e-13, 1e-3 * (double)o.tol))));
         GEMB_TRY(c->t_dense.end(c->stream));
         GEMB_CUDA(cudaMemcpyAsync(theta.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
         GEMB_CUDA(cudaStreamSynchronize(c->stream));
@@ -490,28 +490,21 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
 
     for (int it = 1; it <= o.max_iters; it++) {
         R.iters = it;
-        // Rayleigh-Ritz on A: T = V^T A V on the main stream, its eigen-decomposition (one CTA) on the side stream
+        // Rayleigh-Ritz on A: T = V^T A V, (l, Z) = eigh(T)
         GEMB_TRY(dist_spmm(W, false, b, 1.f, V, nullptr, AV, true));
         GEMB_TRY(gram_full(W, V, AV, W.G2));
         symmetrize_kernel<<<(b * b + 255) / 256, 256, 0, c->stream>>>(b, W.G2);
         GEMB_CUDA(cudaGetLastError());
         count_launch();
-        GEMB_CUDA(cudaEventRecord(c->ev_a, c->stream));
-        GEMB_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_a, 0));
-        {
-            cudaStream_t main_stream = c->stream;
-            c->stream = c->stream2;                                    // eigh_launch uses ctx->stream
-            const int es = eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs);
-            c->stream = main_stream;
-            GEMB_TRY(es);
-        }
-        GEMB_CUDA(cudaMemcpyAsync(lam.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream2));
-        GEMB_CUDA(cudaEventRecord(c->ev_b, c->stream2));
-        // while the Jacobi sweeps run on one SM, start the filter with the interval of the PREVIOUS round
-        // (the damped set only grows from round to round, so the lagged interval is conservative)
+        // (Measured: running the single-CTA Jacobi on a side stream while the filter starts with the PREVIOUS
+        // round's interval costs two extra rounds -- 75 instead of 56 SpMM sweeps -- and is slower overall;
+        // the eigen-decomposition therefore stays on the critical path.)
+        GEMB_TRY(c->t_dense.begin(c->stream));
+        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs, std::min(1e-7, std::max(1e-13, 1e-3 * (double)o.tol))));
+        GEMB_TRY(c->t_dense.end(c->stream));
+        GEMB_CUDA(cudaMemcpyAsync(lam.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
         float *filtered = nullptr;
-        if (plan.valid && plan.deg >= 2 && it < o.max_iters) GEMB_TRY(run_filter(plan, &filtered));
-        GEMB_CUDA(cudaStreamSynchronize(c->stream2));
         if (ritz_bound) {
             double amax = 0.0;
             for (int i = 0; i < b; i++) amax = std::max(amax, fabs(lam[i]));
@@ -555,7 +548,6 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         np.deg = o.cheb_degree;
         if (growth > 1.0 + 1e-9) np.deg = std::min(np.deg, (int)floor(log(2.0 * 256.0) / log(growth)));
 
-        GEMB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));         // Z is needed from here on
         if (!filtered) {
             if (np.deg < 2) {                                          // A V is already there: one power step
                 GEMB_TRY(orth_rotated(W, AV, pool[0], V));
@@ -571,7 +563,6 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
             if (cand != filtered) { tmp = cand; break; }
         GEMB_TRY(orth_rotated(W, filtered, tmp, V));
     }
-    GEMB_CUDA(cudaStreamSynchronize(c->stream));   // a speculative filter of the last round may still be running
 
     // ---- extraction: top k by |f|, ascending sigma
     std::vector<int> sel(order.begin(), order.begin() + k);

@@ -87,6 +87,11 @@ int gemb_spmm(gemb_graph *g, int transpose, int b, float alpha, const float *X, 
 int gemb_gram(gemb_ctx *ctx, int64_t n, const float *P, int b1, const float *Q, int b2, int use_tensor_cores,
               double *G_out);
 
+/* Test hook for the tall-skinny product Out (n x b2) = Q (n x b1) * M (b1 x b2), host fp32 row-major buffers.
+ * use_tensor_cores: 1 = tcgen05 kernel, 0 = CUDA-core kernel. */
+int gemb_apply(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *M, int b2, int use_tensor_cores,
+               float *Out);
+
 /* ---- HOPE.  Replaces hope.py:29-36: S = (I - beta A)^-1 beta A is never formed; its top
  * k = d/2 singular triplets come from a block subspace iteration with Rayleigh-Ritz whose
  * operator applications are CSR SpMM sweeps (Katz/Horner sweeps of S and S^T in general; a Chebyshev

@@ -50,3 +50,24 @@ def test_gram_tc_large_streaming(gpu_ctx):
     d = np.sqrt(np.diag(G32))
     assert np.abs(G - G32).max() / (d.max() ** 2) < 4e-6
     assert np.allclose(np.diag(G), (P.astype(np.float64) ** 2).sum(axis=0), rtol=2e-6)
+
+
+@pytest.mark.parametrize('tc', [True, False])
+@pytest.mark.parametrize('n,b1,b2', [(5000, 80, 80), (70001, 80, 80), (1_000_000, 80, 80), (33000, 96, 64),
+                                     (4100, 128, 128), (9000, 24, 24), (300, 80, 80)])
+def test_apply_kernels(gpu_ctx, n, b1, b2, tc):
+    """Out = Q M (CholeskyQR's Q R^-1, Ritz rotations): tcgen05 3xTF32 kernel and CUDA-core kernel vs NumPy fp64;
+    |Out - ref|_ij <= 4e-6 * ||Q_i|| ||M_j||."""
+    rng = np.random.default_rng(n + b1)
+    Q = rng.standard_normal((n, b1)).astype(np.float32)
+    M = np.triu(rng.standard_normal((b1, b2))).astype(np.float32)
+    try:
+        out = gpu_ctx.apply(Q, M, tensor_cores=tc)
+    except RuntimeError as e:
+        if tc and 'not supported by the tcgen05 kernel' in str(e):
+            pytest.skip('shape outside the tcgen05 kernel')
+        raise
+    ref = Q.astype(np.float64) @ M.astype(np.float64)
+    bound = np.outer(np.linalg.norm(Q.astype(np.float64), axis=1), np.linalg.norm(M.astype(np.float64), axis=0)) + 1e-30
+    err = np.abs(out - ref) / bound
+    assert err.max() < 4e-6, (n, b1, b2, tc, err.max())
