@@ -332,7 +332,10 @@ def run_hope(args, dist, rank, world, local):
                                        'deg 16 in / 4 out, seed 42' % (args.d, args.beta, n, args.n, csr.nnz),
                            'solver': dict(solver, block=stats['block'], katz_terms=stats['katz_terms'],
                                           iters=stats['iters'], converged=stats['converged'],
-                                          ritz_change=stats['ritz_change']),
+                                          ritz_change=stats['ritz_change'],
+                                          algorithm={1: 'subspace iteration on S^T S (Katz sweeps)',
+                                                     2: 'Chebyshev-filtered subspace iteration on A (S = f(A), A symmetric)'}
+                                          .get(stats['algorithm'], stats['algorithm'])),
                            'parallelism': 'row-sharded CSR x%d, all-gather per SpMM' % world if world > 1 else 'single GPU',
                            'l2_policy': 'inputs larger than L2 (CSR %.0f MB + 5 blocks of %.0f MB vs 126 MB L2)' % (
                                (csr.nnz * 4 + csr.n * 4) / 1e6, csr.n * stats['block'] * 4 / 1e6 / world)},
