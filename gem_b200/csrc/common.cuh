@@ -64,6 +64,7 @@ struct gemb_ctx {
     int rank = 0, nranks = 1;
     void *comm = nullptr;  // ncclComm_t
     int *tile_counter = nullptr;  // device work counter of the persistent SpMM kernel
+    int *smq_counters = nullptr;  // per-SM work queues of the SM-affine SpMM kernel
     gemb::Timer t_spmm, t_dense, t_comm, t_misc;
 };
 

@@ -139,6 +139,7 @@ int gemb_ctx_destroy(gemb_ctx *c) {
     c->t_comm.destroy();
     c->t_misc.destroy();
     cudaFree(c->tile_counter);
+    cudaFree(c->smq_counters);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->stream2) cudaStreamDestroy(c->stream2);
