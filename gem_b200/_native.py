@@ -16,7 +16,7 @@ UNIQUE_ID_BYTES = 128
 
 EXPORTS = [
     'gemb_version', 'gemb_last_error', 'gemb_device_count', 'gemb_launch_count', 'gemb_ctx_create', 'gemb_ctx_destroy',
-    'gemb_host_alloc', 'gemb_host_free', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
+    'gemb_host_alloc', 'gemb_host_free', 'gemb_mem_trim', 'gemb_mem_cached_bytes', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
     'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_apply', 'gemb_hope', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
 ]
 
@@ -71,6 +71,9 @@ def lib():
     L.gemb_ctx_destroy.argtypes = [vp]
     L.gemb_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.gemb_host_free.argtypes = [vp]
+    L.gemb_mem_trim.argtypes = []
+    L.gemb_mem_cached_bytes.argtypes = []
+    L.gemb_mem_cached_bytes.restype = ctypes.c_size_t
     L.gemb_comm_unique_id.argtypes = [vp]
     L.gemb_comm_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
     L.gemb_graph_upload.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]
@@ -127,6 +130,15 @@ def pinned_empty(shape, dtype):
     buf._owner = owner          # `buf` is the ultimate .base of every view: the allocation lives as long as any of them
     arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
     return arr.view(PinnedArray)
+
+
+def mem_trim():
+    """Return the cached device work buffers to the driver (gemb_mem_trim)."""
+    check(lib().gemb_mem_trim())
+
+
+def mem_cached_bytes():
+    return int(lib().gemb_mem_cached_bytes())
 
 
 class Context:

@@ -42,6 +42,15 @@ void count_launch(int k = 1);   // every kernel launch of this library is counte
 struct NcclApi;
 NcclApi *nccl_api();  // nullptr (and error set) if libnccl cannot be loaded
 
+// ---- device memory (core.cu).  Released blocks are kept in a per-device free list and handed back on the next
+//      request of the same rounded size (2 MiB granules from 1 MiB up, 512 B below), so a second learn_embedding call on the
+//      same problem shape makes no driver allocation at all (cudaMalloc/cudaFree of 2.5 GB per call cost a
+//      sporadic 100+ ms of page mapping).  GEMB_CACHE_MB caps the cached bytes (0 disables, default 65536);
+//      gemb_mem_trim() releases everything.  dfree keeps cudaFree's implicit device synchronisation.
+cudaError_t dmalloc_bytes(void **p, size_t bytes);
+cudaError_t dfree(void *p);
+template <class T> inline cudaError_t dmalloc(T **p, size_t bytes) { return dmalloc_bytes((void **)p, bytes); }
+
 struct Timer {  // pairs of events on ctx->stream, summed on demand
     std::vector<cudaEvent_t> ev;
     size_t used = 0;
@@ -58,13 +67,10 @@ struct gemb_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;      // side stream: single-CTA factorizations overlapped with SpMM sweeps
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // multi-GPU
     int rank = 0, nranks = 1;
     void *comm = nullptr;  // ncclComm_t
     int *tile_counter = nullptr;  // device work counter of the persistent SpMM kernel
-    int *smq_counters = nullptr;  // per-SM work queues of the SM-affine SpMM kernel
     gemb::Timer t_spmm, t_dense, t_comm, t_misc;
 };
 

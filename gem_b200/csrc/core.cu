@@ -5,6 +5,10 @@
 #include <stdarg.h>
 #include <string.h>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <stdlib.h>
 
 namespace gemb {
 
@@ -77,11 +81,102 @@ NcclApi *nccl_api() {
     return &g_nccl;
 }
 
+// ---- device block cache (see common.cuh).  One free list per device, keyed by rounded size.
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_[64];
+    std::unordered_map<void *, std::pair<size_t, int>> live;   // cached-class blocks handed out: ptr -> (size, device)
+    size_t cached_bytes = 0;
+    long long limit = -1;
+    size_t cap() {
+        if (limit < 0) { const char *e = getenv("GEMB_CACHE_MB"); limit = (e ? atoll(e) : 65536LL) << 20; }
+        return (size_t)limit;
+    }
+    void trim_locked(int dev) {   // dev < 0: all devices
+        int cur = 0; cudaGetDevice(&cur);
+        for (int d = 0; d < 64; d++) {
+            if ((dev >= 0 && d != dev) || free_[d].empty()) continue;
+            cudaSetDevice(d);
+            for (auto &kv : free_[d]) { cudaFree(kv.second); cached_bytes -= kv.first; }
+            free_[d].clear();
+        }
+        cudaSetDevice(cur);
+    }
+};
+BlockCache g_cache;
+const size_t kCacheMin = (size_t)1 << 20, kCacheRound = (size_t)2 << 20;
+}  // namespace
+
+cudaError_t dmalloc_bytes(void **p, size_t bytes) {
+    if (g_cache.cap() == 0) return cudaMalloc(p, bytes ? bytes : 4);
+    const size_t rnd = bytes < kCacheMin ? 512 : kCacheRound;   // small blocks are cached too: fewer driver calls per call
+    const size_t sz = (bytes + rnd - 1) / rnd * rnd + (bytes == 0 ? rnd : 0);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    if (dev < 64) {
+        auto it = g_cache.free_[dev].find(sz);
+        if (it != g_cache.free_[dev].end()) {
+            *p = it->second;
+            g_cache.free_[dev].erase(it);
+            g_cache.cached_bytes -= sz;
+            g_cache.live[*p] = {sz, dev};
+            return cudaSuccess;
+        }
+    }
+    e = cudaMalloc(p, sz);
+    if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back to the driver and retry once
+        (void)cudaGetLastError();
+        g_cache.trim_locked(dev);
+        e = cudaMalloc(p, sz);
+    }
+    if (e == cudaSuccess && dev < 64) g_cache.live[*p] = {sz, dev};
+    return e;
+}
+
+cudaError_t dfree(void *p) {
+    if (!p) return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        auto it = g_cache.live.find(p);
+        if (it != g_cache.live.end()) {
+            const size_t sz = it->second.first;
+            const int dev = it->second.second;
+            g_cache.live.erase(it);
+            if (g_cache.cached_bytes + sz <= g_cache.cap()) {
+                int cur = 0; cudaGetDevice(&cur);
+                if (cur != dev) cudaSetDevice(dev);
+                cudaError_t e = cudaDeviceSynchronize();   // what cudaFree would have done: no kernel still uses the block
+                if (cur != dev) cudaSetDevice(cur);
+                if (e == cudaSuccess) {
+                    g_cache.free_[dev].emplace(sz, p);
+                    g_cache.cached_bytes += sz;
+                    return cudaSuccess;
+                }
+            }
+        }
+    }
+    return cudaFree(p);
+}
+
 }  // namespace gemb
 
 using namespace gemb;
 
 extern "C" {
+
+int gemb_mem_trim(void) {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    g_cache.trim_locked(-1);
+    return GEMB_OK;
+}
+
+size_t gemb_mem_cached_bytes(void) {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    return g_cache.cached_bytes;
+}
 
 int gemb_version(void) { return GEMB_VERSION; }
 int64_t gemb_launch_count(void) { return (int64_t)gemb::launches_total(); }
@@ -116,13 +211,6 @@ int gemb_ctx_create(int device, gemb_ctx **out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     GEMB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    {
-        int lo_prio = 0, hi_prio = 0;   // side stream gets the highest priority: its single CTA must not queue behind 83k SpMM CTAs
-        GEMB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
-        GEMB_CUDA(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi_prio));
-    }
-    GEMB_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
-    GEMB_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     *out = c;
     return GEMB_OK;
 }
@@ -138,11 +226,7 @@ int gemb_ctx_destroy(gemb_ctx *c) {
     c->t_dense.destroy();
     c->t_comm.destroy();
     c->t_misc.destroy();
-    cudaFree(c->tile_counter);
-    cudaFree(c->smq_counters);
-    if (c->ev_a) cudaEventDestroy(c->ev_a);
-    if (c->ev_b) cudaEventDestroy(c->ev_b);
-    if (c->stream2) cudaStreamDestroy(c->stream2);
+    dfree(c->tile_counter);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return GEMB_OK;
@@ -199,15 +283,15 @@ static int upload_csr(gemb_ctx *c, int64_t n_local, const int32_t *indptr, const
     GEMB_ARG(indptr[0] == 0, "indptr[0] must be 0 (shard-local offsets)");
     GEMB_ARG(nnz >= 0 && nnz < (int64_t)2147483647, "nnz per shard must be < 2^31");
     d->nnz = nnz;
-    GEMB_CUDA(cudaMalloc(&d->indptr, sizeof(int32_t) * (n_local + 1)));
-    GEMB_CUDA(cudaMalloc(&d->indices, sizeof(int32_t) * (nnz > 0 ? nnz : 1)));
+    GEMB_CUDA(dmalloc(&d->indptr, sizeof(int32_t) * (n_local + 1)));
+    GEMB_CUDA(dmalloc(&d->indices, sizeof(int32_t) * (nnz > 0 ? nnz : 1)));
     GEMB_CUDA(cudaMemcpyAsync(d->indptr, indptr, sizeof(int32_t) * (n_local + 1),
                               cudaMemcpyHostToDevice, c->stream));
     if (nnz)
         GEMB_CUDA(cudaMemcpyAsync(d->indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice,
                                   c->stream));
     if (data && nnz) {
-        GEMB_CUDA(cudaMalloc(&d->data, sizeof(float) * nnz));
+        GEMB_CUDA(dmalloc(&d->data, sizeof(float) * nnz));
         GEMB_CUDA(cudaMemcpyAsync(d->data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice,
                                   c->stream));
     }
@@ -268,13 +352,13 @@ int gemb_graph_free(gemb_graph *g) {
     if (!g) return GEMB_OK;
     cudaSetDevice(g->ctx->device);
     if (!g->symmetric) {
-        cudaFree(g->AT.indptr);
-        cudaFree(g->AT.indices);
-        cudaFree(g->AT.data);
+        dfree(g->AT.indptr);
+        dfree(g->AT.indices);
+        dfree(g->AT.data);
     }
-    cudaFree(g->A.indptr);
-    cudaFree(g->A.indices);
-    cudaFree(g->A.data);
+    dfree(g->A.indptr);
+    dfree(g->A.indices);
+    dfree(g->A.data);
     delete g;
     return GEMB_OK;
 }

@@ -31,6 +31,7 @@
 // Multi-GPU: rows are sharded; each SpMM is preceded by an all-gather of the block's row shards
 // and each Gram matrix is all-reduced (b x b fp64).
 #include "common.cuh"
+#include <chrono>
 #include "nccl_api.h"
 #include <math.h>
 #include <string.h>
@@ -52,9 +53,9 @@ struct HopeWork {
     int *rank_dev = nullptr;
     int64_t spmm_wide = 0, spmm_all = 0;
     ~HopeWork() {
-        for (auto p : buf) cudaFree(p);
-        cudaFree(full); cudaFree(G); cudaFree(G2); cudaFree(w); cudaFree(Z); cudaFree(Zs); cudaFree(scal);
-        cudaFree(Minv); cudaFree(M1); cudaFree(M2); cudaFree(rank_dev);
+        for (auto p : buf) dfree(p);
+        dfree(full); dfree(G); dfree(G2); dfree(w); dfree(Z); dfree(Zs); dfree(scal);
+        dfree(Minv); dfree(M1); dfree(M2); dfree(rank_dev);
     }
 };
 
@@ -377,7 +378,7 @@ static int hope_general(HopeWork &W, const Opts &o, int d, float beta, int J, Ho
     // extraction: X = [U Z_k theta^-1/4 | V Z_k theta^1/4]; U = S V (un-normalised), V orthonormal
     R.Xd = T1;
     if ((size_t)d > (size_t)b) {
-        GEMB_CUDA(cudaMalloc(&R.Xalloc, sizeof(float) * (size_t)std::max<int64_t>(W.rows, 1) * d));
+        GEMB_CUDA(dmalloc(&R.Xalloc, sizeof(float) * (size_t)std::max<int64_t>(W.rows, 1) * d));
         R.Xd = R.Xalloc;
     }
     GEMB_TRY(c->t_dense.begin(c->stream));
@@ -400,16 +401,16 @@ static int hope_general(HopeWork &W, const Opts &o, int d, float beta, int J, Ho
         float *Pm = Wk, *Qs = nullptr, *Qalloc = nullptr, *STP = nullptr;
         const size_t blk = sizeof(float) * (size_t)W.shard * b;
         if (R.Xalloc) Qs = T1;
-        else { GEMB_CUDA(cudaMalloc(&Qalloc, blk ? blk : 4)); GEMB_CUDA(cudaMemsetAsync(Qalloc, 0, blk, c->stream)); Qs = Qalloc; }
-        GEMB_CUDA(cudaMalloc(&STP, blk ? blk : 4));
+        else { GEMB_CUDA(dmalloc(&Qalloc, blk ? blk : 4)); GEMB_CUDA(cudaMemsetAsync(Qalloc, 0, blk, c->stream)); Qs = Qalloc; }
+        GEMB_CUDA(dmalloc(&STP, blk ? blk : 4));
         GEMB_CUDA(cudaMemsetAsync(STP, 0, blk, c->stream));
         int s = apply_launch(c, W.rows, U, b, W.M1, b, b, Pm, b);
         if (s == GEMB_OK) s = apply_launch(c, W.rows, V, b, W.M2, b, b, Qs, b);
         std::vector<int> cols;
         for (int j = b - k; j < b; j++) cols.push_back(j);
         if (s == GEMB_OK) s = residual_check(W, beta, J, Pm, Qs, STP, U, T2, cols, R.sigma_max, &R.resid_max);
-        cudaFree(STP);
-        cudaFree(Qalloc);
+        dfree(STP);
+        dfree(Qalloc);
         if (s != GEMB_OK) return s;
     }
     return GEMB_OK;
@@ -590,7 +591,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
     GEMB_CUDA(cudaStreamSynchronize(c->stream));                      // host staging vectors go out of scope
     R.Xd = pool[0];
     if ((size_t)d > (size_t)b) {
-        GEMB_CUDA(cudaMalloc(&R.Xalloc, sizeof(float) * (size_t)std::max<int64_t>(W.rows, 1) * d));
+        GEMB_CUDA(dmalloc(&R.Xalloc, sizeof(float) * (size_t)std::max<int64_t>(W.rows, 1) * d));
         R.Xd = R.Xalloc;
     }
     GEMB_TRY(c->t_dense.begin(c->stream));
@@ -613,11 +614,11 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         }
         float *dMP = nullptr, *dMQ = nullptr, *P = nullptr, *Q = nullptr, *STP = nullptr;
         const size_t blk = sizeof(float) * (size_t)W.shard * b;
-        GEMB_CUDA(cudaMalloc(&dMP, sizeof(float) * b * b));
-        GEMB_CUDA(cudaMalloc(&dMQ, sizeof(float) * b * b));
-        GEMB_CUDA(cudaMalloc(&P, blk ? blk : 4));
-        GEMB_CUDA(cudaMalloc(&Q, blk ? blk : 4));
-        GEMB_CUDA(cudaMalloc(&STP, blk ? blk : 4));
+        GEMB_CUDA(dmalloc(&dMP, sizeof(float) * b * b));
+        GEMB_CUDA(dmalloc(&dMQ, sizeof(float) * b * b));
+        GEMB_CUDA(dmalloc(&P, blk ? blk : 4));
+        GEMB_CUDA(dmalloc(&Q, blk ? blk : 4));
+        GEMB_CUDA(dmalloc(&STP, blk ? blk : 4));
         GEMB_CUDA(cudaMemsetAsync(P, 0, blk, c->stream));
         GEMB_CUDA(cudaMemsetAsync(Q, 0, blk, c->stream));
         GEMB_CUDA(cudaMemsetAsync(STP, 0, blk, c->stream));
@@ -627,7 +628,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         if (s == GEMB_OK) s = apply_launch(c, W.rows, V, b, dMQ, b, b, Q, b);
         if (s == GEMB_OK) s = residual_check(W, beta, J, P, Q, STP, AV, pool[1], sel, R.sigma_max, &R.resid_max);
         cudaStreamSynchronize(c->stream);
-        cudaFree(dMP); cudaFree(dMQ); cudaFree(P); cudaFree(Q); cudaFree(STP);
+        dfree(dMP); dfree(dMQ); dfree(P); dfree(Q); dfree(STP);
         if (s != GEMB_OK) return s;
     }
     return GEMB_OK;
@@ -672,26 +673,30 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     int b = (int)((bb + 3) / 4 * 4);
     GEMB_ARG(b <= 1024, "block width d/2 + oversample must be <= 1024");
 
+    static const bool trace = getenv("GEMB_TRACE") != nullptr;   // host wall clock of the call's stages, to stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_enter = now();
     HopeWork W;
     W.g = g; W.c = c; W.b = b; W.rows = g->n_local; W.shard = g->n_shard;
     const size_t blk = sizeof(float) * (size_t)W.shard * b;
     for (int i = 0; i < 5; i++) {
-        GEMB_CUDA(cudaMalloc(&W.buf[i], blk ? blk : 4));
+        GEMB_CUDA(dmalloc(&W.buf[i], blk ? blk : 4));
         GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));  // padded rows stay 0
     }
-    if (c->nranks > 1) GEMB_CUDA(cudaMalloc(&W.full, sizeof(float) * (size_t)g->n_pad * b));
-    GEMB_CUDA(cudaMalloc(&W.G, sizeof(double) * b * b));
-    GEMB_CUDA(cudaMalloc(&W.G2, sizeof(double) * b * b));
-    GEMB_CUDA(cudaMalloc(&W.Z, sizeof(double) * b * b));
-    GEMB_CUDA(cudaMalloc(&W.Zs, sizeof(double) * b * b));
-    GEMB_CUDA(cudaMalloc(&W.w, sizeof(double) * b));
-    GEMB_CUDA(cudaMalloc(&W.scal, sizeof(double) * (b + 8)));
-    GEMB_CUDA(cudaMalloc(&W.Minv, sizeof(float) * b * b));
-    GEMB_CUDA(cudaMalloc(&W.M1, sizeof(float) * b * b));
-    GEMB_CUDA(cudaMalloc(&W.M2, sizeof(float) * b * b));
-    GEMB_CUDA(cudaMalloc(&W.rank_dev, sizeof(int)));
+    if (c->nranks > 1) GEMB_CUDA(dmalloc(&W.full, sizeof(float) * (size_t)g->n_pad * b));
+    GEMB_CUDA(dmalloc(&W.G, sizeof(double) * b * b));
+    GEMB_CUDA(dmalloc(&W.G2, sizeof(double) * b * b));
+    GEMB_CUDA(dmalloc(&W.Z, sizeof(double) * b * b));
+    GEMB_CUDA(dmalloc(&W.Zs, sizeof(double) * b * b));
+    GEMB_CUDA(dmalloc(&W.w, sizeof(double) * b));
+    GEMB_CUDA(dmalloc(&W.scal, sizeof(double) * (b + 8)));
+    GEMB_CUDA(dmalloc(&W.Minv, sizeof(float) * b * b));
+    GEMB_CUDA(dmalloc(&W.M1, sizeof(float) * b * b));
+    GEMB_CUDA(dmalloc(&W.M2, sizeof(float) * b * b));
+    GEMB_CUDA(dmalloc(&W.rank_dev, sizeof(int)));
 
     c->t_spmm.reset(); c->t_dense.reset(); c->t_comm.reset(); c->t_misc.reset();
+    const double t_alloc = now();
     cudaEvent_t ev0, ev1;
     GEMB_CUDA(cudaEventCreate(&ev0));
     GEMB_CUDA(cudaEventCreate(&ev1));
@@ -721,13 +726,14 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
 
     HopeResult R;
     int s = (algo == 2) ? hope_symmetric(W, o, d, beta, nrm, hard_bound, R) : hope_general(W, o, d, beta, J, R);
-    if (s != GEMB_OK) { cudaFree(R.Xalloc); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return s; }
+    if (s != GEMB_OK) { dfree(R.Xalloc); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return s; }
 
     GEMB_CUDA(cudaEventRecord(ev1, c->stream));
     GEMB_CUDA(cudaEventSynchronize(ev1));
     float total_ms = 0.f;
     GEMB_CUDA(cudaEventElapsedTime(&total_ms, ev0, ev1));
 
+    const double t_solve = now();
     double d2h_ms = 0.0;
     if (X_out || sigma_out) {
         cudaEvent_t e2, e3;
@@ -740,8 +746,11 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         float ms = 0.f; cudaEventElapsedTime(&ms, e2, e3); d2h_ms = ms;
         cudaEventDestroy(e2); cudaEventDestroy(e3);
     }
-    cudaFree(R.Xalloc);
+    dfree(R.Xalloc);
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (trace)
+        fprintf(stderr, "[gemb_hope] host ms: alloc %.2f  solve %.2f (device %.2f)  d2h %.2f (device %.2f)\n",
+                t_alloc - t_enter, t_solve - t_alloc, total_ms, now() - t_solve, d2h_ms);
 
     if (stats) {
         stats->iters = R.iters;

@@ -426,9 +426,9 @@ struct N2VDev {
     float *syn_pos = nullptr, *syn_neg = nullptr, *pos0 = nullptr, *delta = nullptr;
     uint32_t *seq_state = nullptr;
     ~N2VDev() {
-        cudaFree(w); cudaFree(U); cudaFree(K); cudaFree(scratch); cudaFree(order); cudaFree(walks);
-        cudaFree(first_pos); cudaFree(cnt); cudaFree(pairs); cudaFree(KT); cudaFree(tok2node); cudaFree(UT); cudaFree(ent);
-        cudaFree(syn_pos); cudaFree(syn_neg); cudaFree(pos0); cudaFree(delta); cudaFree(seq_state);
+        dfree(w); dfree(U); dfree(K); dfree(scratch); dfree(order); dfree(walks);
+        dfree(first_pos); dfree(cnt); dfree(pairs); dfree(KT); dfree(tok2node); dfree(UT); dfree(ent);
+        dfree(syn_pos); dfree(syn_neg); dfree(pos0); dfree(delta); dfree(seq_state);
     }
 };
 
@@ -441,11 +441,11 @@ static int check_graph_for_n2v(gemb_graph *g) {
 static int build_alias(gemb_graph *g, const double *weights64, N2VDev &D) {
     gemb_ctx *c = g->ctx;
     const int64_t nnz = g->A.nnz;
-    GEMB_CUDA(cudaMalloc(&D.K, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
-    GEMB_CUDA(cudaMalloc(&D.U, sizeof(double) * std::max<int64_t>(nnz, 1)));
-    GEMB_CUDA(cudaMalloc(&D.scratch, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+    GEMB_CUDA(dmalloc(&D.K, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+    GEMB_CUDA(dmalloc(&D.U, sizeof(double) * std::max<int64_t>(nnz, 1)));
+    GEMB_CUDA(dmalloc(&D.scratch, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
     if (weights64 && nnz) {
-        GEMB_CUDA(cudaMalloc(&D.w, sizeof(double) * nnz));
+        GEMB_CUDA(dmalloc(&D.w, sizeof(double) * nnz));
         GEMB_CUDA(cudaMemcpyAsync(D.w, weights64, sizeof(double) * nnz, cudaMemcpyHostToDevice, c->stream));
     }
     const int64_t n = g->n;
@@ -467,10 +467,10 @@ static int run_walks(gemb_graph *g, N2VDev &D, const int32_t *nids, int64_t N, i
     std::vector<int32_t> order((size_t)num_walks * N);
     shuffle_rounds(nids, N, num_walks, walk_len, seed, order.data());
     if (shuffle_ms) *shuffle_ms = ms_since(t0);
-    GEMB_CUDA(cudaMalloc(&D.order, sizeof(int32_t) * std::max<size_t>(order.size(), 1)));
+    GEMB_CUDA(dmalloc(&D.order, sizeof(int32_t) * std::max<size_t>(order.size(), 1)));
     GEMB_CUDA(cudaMemcpyAsync(D.order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice, c->stream));
     const int64_t cnt = w_end - w_begin;
-    GEMB_CUDA(cudaMalloc(&D.walks, sizeof(int32_t) * std::max<int64_t>(cnt * walk_len, 1)));
+    GEMB_CUDA(dmalloc(&D.walks, sizeof(int32_t) * std::max<int64_t>(cnt * walk_len, 1)));
     if (cnt > 0) {
         walk_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, c->stream>>>(g->A.indptr, g->A.indices, D.K, D.U, D.order,
                                                                          N, walk_len, seed, w_begin, w_end, D.walks);
@@ -611,8 +611,8 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
     // ---- vocabulary: first appearance + counts (all ranks combined), host renumbering + Vose
     auto tv0 = std::chrono::steady_clock::now();
     const int64_t n_ids = g->n;
-    GEMB_CUDA(cudaMalloc(&D.first_pos, sizeof(unsigned long long) * n_ids));
-    GEMB_CUDA(cudaMalloc(&D.cnt, sizeof(unsigned long long) * n_ids));
+    GEMB_CUDA(dmalloc(&D.first_pos, sizeof(unsigned long long) * n_ids));
+    GEMB_CUDA(dmalloc(&D.cnt, sizeof(unsigned long long) * n_ids));
     GEMB_CUDA(cudaMemsetAsync(D.first_pos, 0xff, sizeof(unsigned long long) * n_ids, c->stream));
     GEMB_CUDA(cudaMemsetAsync(D.cnt, 0, sizeof(unsigned long long) * n_ids, c->stream));
     if (n_local > 0) {
@@ -654,11 +654,11 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
         while (t < 2147483647LL && (double)t / 2147483647.0 < u) t++;
         ent[i] = make_uint4((uint32_t)t, (uint32_t)tok2node[i], (uint32_t)tok2node[KT[i]], 0u);
     }
-    GEMB_CUDA(cudaMalloc(&D.ent, sizeof(uint4) * V));
+    GEMB_CUDA(dmalloc(&D.ent, sizeof(uint4) * V));
     GEMB_CUDA(cudaMemcpyAsync(D.ent, ent.data(), sizeof(uint4) * V, cudaMemcpyHostToDevice, c->stream));
-    GEMB_CUDA(cudaMalloc(&D.KT, sizeof(int32_t) * V));
-    GEMB_CUDA(cudaMalloc(&D.UT, sizeof(double) * V));
-    GEMB_CUDA(cudaMalloc(&D.tok2node, sizeof(int32_t) * V));
+    GEMB_CUDA(dmalloc(&D.KT, sizeof(int32_t) * V));
+    GEMB_CUDA(dmalloc(&D.UT, sizeof(double) * V));
+    GEMB_CUDA(dmalloc(&D.tok2node, sizeof(int32_t) * V));
     GEMB_CUDA(cudaMemcpyAsync(D.KT, KT.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, c->stream));
     GEMB_CUDA(cudaMemcpyAsync(D.UT, UT.data(), sizeof(double) * V, cudaMemcpyHostToDevice, c->stream));
     GEMB_CUDA(cudaMemcpyAsync(D.tok2node, tok2node.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, c->stream));
@@ -668,24 +668,24 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
 
     // ---- embeddings
     const size_t tab = (size_t)n_rows * d;
-    GEMB_CUDA(cudaMalloc(&D.syn_pos, sizeof(float) * tab));
-    GEMB_CUDA(cudaMalloc(&D.syn_neg, sizeof(float) * tab));
+    GEMB_CUDA(dmalloc(&D.syn_pos, sizeof(float) * tab));
+    GEMB_CUDA(dmalloc(&D.syn_neg, sizeof(float) * tab));
     GEMB_CUDA(cudaMemsetAsync(D.syn_pos, 0, sizeof(float) * tab, c->stream));
     GEMB_CUDA(cudaMemsetAsync(D.syn_neg, 0, sizeof(float) * tab, c->stream));
     init_pos_kernel<<<(unsigned)((V + 127) / 128), 128, 0, c->stream>>>(V, d, (uint32_t)seed, D.tok2node, D.syn_pos);
     GEMB_CUDA(cudaGetLastError());
     count_launch();
-    GEMB_CUDA(cudaMalloc(&D.pairs, sizeof(unsigned long long)));
+    GEMB_CUDA(dmalloc(&D.pairs, sizeof(unsigned long long)));
     GEMB_CUDA(cudaMemsetAsync(D.pairs, 0, sizeof(unsigned long long), c->stream));
-    GEMB_CUDA(cudaMalloc(&D.seq_state, sizeof(uint32_t)));
+    GEMB_CUDA(dmalloc(&D.seq_state, sizeof(uint32_t)));
     {
         const uint32_t st0 = lcg_skip((uint32_t)seed, (uint64_t)V * (uint64_t)d);  // after InitPosEmb's V*d draws
         GEMB_CUDA(cudaMemcpyAsync(D.seq_state, &st0, sizeof st0, cudaMemcpyHostToDevice, c->stream));
         GEMB_CUDA(cudaStreamSynchronize(c->stream));
     }
     if (c->nranks > 1) {
-        GEMB_CUDA(cudaMalloc(&D.pos0, sizeof(float) * tab));
-        GEMB_CUDA(cudaMalloc(&D.delta, sizeof(float) * tab));
+        GEMB_CUDA(dmalloc(&D.pos0, sizeof(float) * tab));
+        GEMB_CUDA(dmalloc(&D.delta, sizeof(float) * tab));
     }
 
     SgnsParams P;

@@ -147,87 +147,14 @@ spmm_tile_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__
     }
 }
 
-// ---- v3: v1's shape (256-thread CTAs, full occupancy) but SM-affine work: every SM owns a queue of row TILES
-// (tile t belongs to queue t % S); a CTA reads %smid, grabs a few consecutive row groups of its SM's current
-// tile with one atomicAdd, and steals from the other queues when its own is empty (so every row is processed
-// whatever the CTA -> SM placement is).  All CTAs resident on an SM then gather from the same neighbourhood.
-template <bool HAS_VAL, bool HAS_X0, bool HAS_SELF>
-__global__ void __launch_bounds__(256)
-spmm_smq_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
-                const float *__restrict__ vals, int64_t n_rows, int G, int rpg /* rows per group */,
-                int gpt /* groups per tile */, int chunk /* groups per grab */, int n_tiles, int S,
-                float alpha, float gamma, float delta, const float4 *__restrict__ X,
-                const float4 *__restrict__ Xself, const float4 *__restrict__ X0,
-                float4 *__restrict__ Y, int *__restrict__ counters) {
-    __shared__ int s_grab[2];
-    const int tid = threadIdx.x;
-    const int lr = tid / G;
-    const int c = tid - lr * G;
-    const bool active = lr < rpg;
-    const float4 *Xc = X + c;
-    unsigned smid;
-    asm("mov.u32 %0, %%smid;" : "=r"(smid));
-    const int grabs_per_tile = (gpt + chunk - 1) / chunk;
-    const int tile_rows = gpt * rpg;
-    int q = (int)(smid % (unsigned)S);
-    int visited = 0, it = 0;
-    while (visited < S) {
-        if (tid == 0) s_grab[it & 1] = atomicAdd(counters + q, 1);
-        __syncthreads();
-        const int g = s_grab[it & 1];
-        it++;
-        const int tile = q + (g / grabs_per_tile) * S;
-        if (tile >= n_tiles) { q = q + 1 == S ? 0 : q + 1; visited++; continue; }   // queue empty: steal from the next
-        const int g0 = (g % grabs_per_tile) * chunk;
-        const int g1 = g0 + chunk < gpt ? g0 + chunk : gpt;
-        if (!active) continue;
-        for (int gi = g0; gi < g1; gi++) {
-            const int64_t row = (int64_t)tile * tile_rows + (int64_t)gi * rpg + lr;
-            if (row >= n_rows) break;
-            const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            int i = s;
-            for (; i + 4 <= e; i += 4) {
-                const int c0 = __ldg(indices + i), c1 = __ldg(indices + i + 1);
-                const int c2 = __ldg(indices + i + 2), c3 = __ldg(indices + i + 3);
-                float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
-                if (HAS_VAL) {
-                    v0 = __ldg(vals + i); v1 = __ldg(vals + i + 1);
-                    v2 = __ldg(vals + i + 2); v3 = __ldg(vals + i + 3);
-                }
-                const float4 x0 = __ldg(Xc + (int64_t)c0 * G);
-                const float4 x1 = __ldg(Xc + (int64_t)c1 * G);
-                const float4 x2 = __ldg(Xc + (int64_t)c2 * G);
-                const float4 x3 = __ldg(Xc + (int64_t)c3 * G);
-                fma4(acc, v0, x0); fma4(acc, v1, x1); fma4(acc, v2, x2); fma4(acc, v3, x3);
-            }
-            for (; i < e; i++) {
-                const int c0 = __ldg(indices + i);
-                const float v0 = HAS_VAL ? __ldg(vals + i) : 1.f;
-                fma4(acc, v0, __ldg(Xc + (int64_t)c0 * G));
-            }
-            float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
-            if (HAS_SELF) {
-                const float4 z = __ldg(Xself + row * G + c);
-                r.x = fmaf(gamma, z.x, r.x); r.y = fmaf(gamma, z.y, r.y);
-                r.z = fmaf(gamma, z.z, r.z); r.w = fmaf(gamma, z.w, r.w);
-            }
-            if (HAS_X0) {
-                const float4 z = __ldg(X0 + row * G + c);
-                r.x = fmaf(delta, z.x, r.x); r.y = fmaf(delta, z.y, r.y);
-                r.z = fmaf(delta, z.z, r.z); r.w = fmaf(delta, z.w, r.w);
-            }
-            Y[row * G + c] = r;
-        }
-    }
-}
-
 // Measured on B200 (SBM 1M / 20M, b = 80): v2 is SLOWER than v1 (0.73-0.84 ms vs 0.56 ms per sweep for tiles of
 // 256-2048 rows): halving the resident threads costs more than the L1 hits buy.  v1 stays the default;
 // GEMB_SPMM=v2 selects this kernel for experiments, GEMB_SPMM_TILE=<rows> sets its tile.
+// A third shape -- v1's 256-thread CTAs with SM-affine tile queues (%smid-keyed atomic counters, stealing) so that
+// the CTAs sharing an L1 work on neighbouring rows -- measured 0.76-0.84 ms per sweep and was removed.
 static int spmm_variant() {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("GEMB_SPMM"); v = (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '3') ? e[1] - '0' : 1; }
+    if (v < 0) { const char *e = getenv("GEMB_SPMM"); v = (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '2') ? e[1] - '0' : 1; }
     return v;
 }
 static int spmm_tile_rows() {
@@ -247,7 +174,7 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
     if (n_rows == 0) return GEMB_OK;
     const int G = b / 4;
     if (spmm_variant() == 2 && n_rows >= 65536 && G <= 256) {
-        if (!ctx->tile_counter) GEMB_CUDA(cudaMalloc(&ctx->tile_counter, sizeof(int)));
+        if (!ctx->tile_counter) GEMB_CUDA(dmalloc(&ctx->tile_counter, sizeof(int)));
         GEMB_CUDA(cudaMemsetAsync(ctx->tile_counter, 0, sizeof(int), ctx->stream));
         const int groups = 1024 / G, tile_rows = spmm_tile_rows();
         const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
@@ -270,39 +197,6 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
             default: LAUNCH2(true, true, true); break;
         }
 #undef LAUNCH2
-        GEMB_CUDA(cudaGetLastError());
-        count_launch();
-        return GEMB_OK;
-    }
-    if (spmm_variant() == 3 && n_rows >= 65536 && G <= 128) {
-        const int S = ctx->sm_count;
-        if (!ctx->smq_counters) GEMB_CUDA(cudaMalloc(&ctx->smq_counters, sizeof(int) * S));
-        GEMB_CUDA(cudaMemsetAsync(ctx->smq_counters, 0, sizeof(int) * S, ctx->stream));
-        const int rpg = 256 / G;
-        int gpt = spmm_tile_rows() / rpg;
-        if (gpt < 4) gpt = 4;
-        const int chunk = 4;
-        const int64_t tile_rows = (int64_t)gpt * rpg;
-        const int n_tiles = (int)((n_rows + tile_rows - 1) / tile_rows);
-        const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0, *XS4 = (const float4 *)Xself;
-        float4 *Y4 = (float4 *)Y;
-        const int grid3 = S * 8;
-#define LAUNCH3(V, Z, SF)                                                                                       \
-        spmm_smq_kernel<V, Z, SF><<<grid3, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G, rpg, gpt, \
-                                                                  chunk, n_tiles, S, alpha, gamma, delta, X4, XS4,  \
-                                                                  X04, Y4, ctx->smq_counters)
-        const int sel3 = (A.data ? 4 : 0) | (X0 ? 2 : 0) | (Xself ? 1 : 0);
-        switch (sel3) {
-            case 0: LAUNCH3(false, false, false); break;
-            case 1: LAUNCH3(false, false, true); break;
-            case 2: LAUNCH3(false, true, false); break;
-            case 3: LAUNCH3(false, true, true); break;
-            case 4: LAUNCH3(true, false, false); break;
-            case 5: LAUNCH3(true, false, true); break;
-            case 6: LAUNCH3(true, true, false); break;
-            default: LAUNCH3(true, true, true); break;
-        }
-#undef LAUNCH3
         GEMB_CUDA(cudaGetLastError());
         count_launch();
         return GEMB_OK;
@@ -345,9 +239,9 @@ extern "C" int gemb_spmm(gemb_graph *g, int transpose, int b, float alpha, const
     GEMB_CUDA(cudaSetDevice(c->device));
     float *dX = nullptr, *dX0 = nullptr, *dY = nullptr;
     const size_t full = sizeof(float) * (size_t)g->n * b, shard = sizeof(float) * (size_t)g->n_local * b;
-    GEMB_CUDA(cudaMalloc(&dX, full ? full : 4));
-    GEMB_CUDA(cudaMalloc(&dY, shard ? shard : 4));
-    if (X0) GEMB_CUDA(cudaMalloc(&dX0, shard ? shard : 4));
+    GEMB_CUDA(dmalloc(&dX, full ? full : 4));
+    GEMB_CUDA(dmalloc(&dY, shard ? shard : 4));
+    if (X0) GEMB_CUDA(dmalloc(&dX0, shard ? shard : 4));
     GEMB_CUDA(cudaMemcpyAsync(dX, X, full, cudaMemcpyHostToDevice, c->stream));
     if (X0) GEMB_CUDA(cudaMemcpyAsync(dX0, X0, shard, cudaMemcpyHostToDevice, c->stream));
     int s = spmm_launch(c, transpose ? g->AT : g->A, g->n_local, b, alpha, dX, dX0, dY);
@@ -359,8 +253,8 @@ extern "C" int gemb_spmm(gemb_graph *g, int transpose, int b, float alpha, const
             s = GEMB_ERR_CUDA;
         }
     }
-    cudaFree(dX);
-    cudaFree(dY);
-    cudaFree(dX0);
+    dfree(dX);
+    dfree(dY);
+    dfree(dX0);
     return s;
 }

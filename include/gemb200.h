@@ -53,6 +53,14 @@ int gemb_ctx_destroy(gemb_ctx *ctx);
 int gemb_host_alloc(size_t bytes, void **out);
 int gemb_host_free(void *p);
 
+/* Device work buffers of one call (the CSR arrays, the n x (d/2+p) blocks) are kept in a per-device free
+ * list when the call returns, so that the next learn_embedding on the same problem shape makes no driver
+ * allocation (the reference re-allocates everything per call, hope.py:26-34; at 2.5 GB per call the
+ * driver's page mapping costs more than the solve).  GEMB_CACHE_MB caps the list (0 = off).
+ * gemb_mem_trim returns every cached block to the driver; gemb_mem_cached_bytes reports the list. */
+int gemb_mem_trim(void);
+size_t gemb_mem_cached_bytes(void);
+
 /* ---- multi-GPU: one process per GPU; rank 0 makes the id, every rank calls init.
  * (No reference counterpart: GEM is single-process) */
 #define GEMB_UNIQUE_ID_BYTES 128

@@ -143,3 +143,22 @@ def test_large_sparse_input_properties(gpu_ctx, hope_oracle, algorithm):
     Xo, so, _ = ho.hope_sparse(A, 16, 0.01, tol=1e-6)
     assert np.allclose(sig[-1], so[-1], rtol=1e-5)               # isolated top value
     assert np.allclose(sig, so, rtol=2e-3)                       # clustered community values
+
+
+def test_work_buffers_are_reused_between_calls(gpu_ctx):
+    """Two learn_embedding calls on the same shape: the second is served from the device block cache
+    (gemb_mem_cached_bytes > 0 between the calls), gives bit-identical output although its buffers hold the
+    previous call's data, and gemb_mem_trim empties the cache."""
+    from gem_b200 import _native, synth
+    csr = synth.sbm(n=120_000, block=1000, seed=3)
+    m = _fresh_hope(d=32, beta=0.01, tol=1e-6, max_iters=40)
+    X1 = m.learn_embedding(graph=csr).copy()
+    cached = _native.mem_cached_bytes()
+    assert cached >= 5 * 120_000 * 32 * 4            # at least the five n x b work blocks
+    X2 = m.learn_embedding(graph=csr)
+    assert np.array_equal(X1, X2)
+    assert _native.mem_cached_bytes() == cached      # nothing new was allocated for the second call
+    _native.mem_trim()
+    assert _native.mem_cached_bytes() == 0
+    X3 = m.learn_embedding(graph=csr)
+    assert np.array_equal(X1, X3)
