@@ -340,6 +340,7 @@ chol_inverse_fast_kernel(int b, const double *__restrict__ Gg, float *__restrict
         G[i * ld + j] = Gg[idx] * dscale[i] * dscale[j];
     }
     __syncthreads();
+    const int gi0 = tid / b, gk0 = tid - gi0 * b, gdi = nt / b, gdk = nt - gdi * b;
     for (int j = 0; j < b; j++) {
         const int m = b - j - 1;
         if (tid < m || tid == 0) {   // the column's owners each derive the pivot (no broadcast barrier)
@@ -356,9 +357,11 @@ chol_inverse_fast_kernel(int b, const double *__restrict__ Gg, float *__restrict
             }
         }
         __syncthreads();
-        for (int idx = tid; idx < m * m; idx += nt) {
-            const int ii = idx / m, kk = idx - ii * m;
-            if (kk <= ii) G[(j + 1 + ii) * ld + (j + 1 + kk)] -= colj[j + 1 + ii] * colj[j + 1 + kk];
+        // every thread owns the same (i, k) positions of the b x b grid in all steps (no index division)
+        for (int i = gi0, k = gk0; i < b;) {
+            if (k > j && k <= i) G[i * ld + k] -= colj[i] * colj[k];
+            k += gdk; i += gdi;
+            if (k >= b) { k -= b; i++; }
         }
         __syncthreads();
     }
@@ -533,24 +536,27 @@ eigh_jacobi_kernel(int b, double *__restrict__ Ag, double *__restrict__ w, doubl
     }
 }
 
-// Fast variant for b*(b|1)*16 bytes <= shared memory (b <= 112): the matrix and the TRANSPOSED eigenvector
-// accumulator live in shared memory with an ODD leading dimension, so that both the column walk (A <- A J:
-// consecutive threads take consecutive rows of one rotated column pair) and the row walks (A <- J^T A,
-// Z^T <- J^T Z^T: consecutive threads take consecutive columns) are bank-conflict free.  The generic kernel's
-// column phase ran 4-5 way conflicted and touched Z column-wise too: 3.9 us per round -> measured below.
+// Fast variant for b*(b|1)*16 bytes <= shared memory (b <= 112).  The generic kernel is ISSUE bound, not
+// bandwidth bound (ncu: 558 warp instructions per warp per round, 63 % issue-active, fp64 pipe 11 %): runtime
+// integer divisions and four parameter loads per element.  Here
+//   * the two-sided update A <- J^T A J is done per 2x2 BLOCK {p,q} x {r,s} of two rotation pairs by one thread
+//     (4 loads, both rotations in registers, 4 stores): half the shared-memory traffic and one block barrier per
+//     round less than column phase + row phase;
+//   * the eigenvector accumulator is kept transposed so that its update is a row walk;
+//   * (pair, column) indices advance incrementally (no division in the loops), rotation parameters are one
+//     16-byte and one 8-byte load, the leading dimension is odd (conflict-free row and column walks).
 __global__ void __launch_bounds__(1024)
 eigh_jacobi_fast_kernel(int b, const double *__restrict__ Ag, double *__restrict__ w, double *__restrict__ Z,
                         int max_sweeps, double rel_tol) {
-    extern __shared__ double sh[];
+    extern __shared__ __align__(16) unsigned char sh_fast[];
+    double *sh = (double *)sh_fast;
     const int m = (b + 1) & ~1;
     const int half = m / 2;
     const int ld = b | 1;
-    double *cs = sh;                // half
-    double *sn = sh + half;         // half
-    int *pp = (int *)(sh + 2 * half);
-    int *qq = pp + half;
-    double *A = sh + 3 * half + 2;  // b x ld
-    double *ZT = A + (size_t)b * ld;   // ZT[j][k] = component k of eigenvector j
+    double2 *csn = (double2 *)sh;                 // half : (c, s)
+    int2 *pq = (int2 *)(sh + 2 * half);           // half : (p, q), q = -1 for the dummy partner
+    double *A = sh + 3 * half + 2;                // b x ld
+    double *ZT = A + (size_t)b * ld;              // ZT[j][k] = component k of eigenvector j
     __shared__ double s_off, s_diag;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int idx = tid; idx < b * b; idx += nt) {
@@ -558,15 +564,19 @@ eigh_jacobi_fast_kernel(int b, const double *__restrict__ Ag, double *__restrict
         A[i * ld + j] = Ag[idx];
         ZT[i * ld + j] = (i == j) ? 1.0 : 0.0;
     }
+    // incremental (pair, column) walks: idx = tid + t * nt  ->  (idx / div, idx % div)
+    const int zb_i0 = tid / b, zb_k0 = tid - zb_i0 * b, zb_di = nt / b, zb_dk = nt - zb_di * b;
+    const int bl_i0 = tid / half, bl_j0 = tid - bl_i0 * half, bl_di = nt / half, bl_dj = nt - bl_di * half;
     __syncthreads();
     for (int sweep = 0; sweep < max_sweeps; sweep++) {
         if (tid == 0) { s_off = 0.0; s_diag = 0.0; }
         __syncthreads();
         double off = 0.0, dg = 0.0;
-        for (int idx = tid; idx < b * b; idx += nt) {
-            const int i = idx / b, j = idx - i * b;
+        for (int i = zb_i0, j = zb_k0; i < b;) {
             const double v = A[i * ld + j];
             if (i == j) dg += v * v; else off += v * v;
+            j += zb_dk; i += zb_di;
+            if (j >= b) { j -= b; i++; }
         }
         for (int o = 16; o > 0; o >>= 1) {
             off += __shfl_xor_sync(0xffffffffu, off, o);
@@ -592,33 +602,44 @@ eigh_jacobi_fast_kernel(int b, const double *__restrict__ Ag, double *__restrict
                         s = t * c;
                     }
                 } else { q = -1; }
-                pp[tid] = p; qq[tid] = q; cs[tid] = c; sn[tid] = s;
+                pq[tid] = make_int2(p, q);
+                csn[tid] = make_double2(c, s);
             }
             __syncthreads();
-            // A <- A J (column pair p,q; consecutive threads = consecutive rows) and Z^T <- J^T Z^T (row pair)
-            for (int idx = tid; idx < 2 * half * b; idx += nt) {
-                const bool zpart = idx >= half * b;
-                const int id2 = zpart ? idx - half * b : idx;
-                const int pi = id2 / b, k = id2 - pi * b;
-                const int p = pp[pi], q = qq[pi];
-                const double c = cs[pi], s = sn[pi];
-                if (q < 0 || s == 0.0) continue;
-                double *xp = zpart ? ZT + p * ld + k : A + k * ld + p;
-                double *yp = zpart ? ZT + q * ld + k : A + k * ld + q;
-                const double x = *xp, y = *yp;
-                *xp = c * x - s * y;
-                *yp = s * x + c * y;
+            // A <- J^T A J, one 2x2 block {p,q} x {r2,s2} per thread
+            for (int pi = bl_i0, rj = bl_j0; pi < half;) {
+                const double2 r1 = csn[pi], r2 = csn[rj];
+                if (r1.y != 0.0 || r2.y != 0.0) {
+                    const int2 a = pq[pi], c2 = pq[rj];
+                    const bool hq = a.y >= 0, hs = c2.y >= 0;
+                    double *row_p = A + a.x * ld, *row_q = A + (hq ? a.y : a.x) * ld;
+                    const int cr = c2.x, cs2 = hs ? c2.y : c2.x;
+                    const double apr = row_p[cr], aps = hs ? row_p[cs2] : 0.0;
+                    const double aqr = hq ? row_q[cr] : 0.0, aqs = (hq && hs) ? row_q[cs2] : 0.0;
+                    const double tpr = r1.x * apr - r1.y * aqr, tqr = r1.y * apr + r1.x * aqr;
+                    const double tps = r1.x * aps - r1.y * aqs, tqs = r1.y * aps + r1.x * aqs;
+                    row_p[cr] = r2.x * tpr - r2.y * tps;
+                    if (hs) row_p[cs2] = r2.y * tpr + r2.x * tps;
+                    if (hq) {
+                        row_q[cr] = r2.x * tqr - r2.y * tqs;
+                        if (hs) row_q[cs2] = r2.y * tqr + r2.x * tqs;
+                    }
+                }
+                rj += bl_dj; pi += bl_di;
+                if (rj >= half) { rj -= half; pi++; }
             }
-            __syncthreads();
-            // A <- J^T A (row pair)
-            for (int idx = tid; idx < half * b; idx += nt) {
-                const int pi = idx / b, k = idx - pi * b;
-                const int p = pp[pi], q = qq[pi];
-                const double c = cs[pi], s = sn[pi];
-                if (q < 0 || s == 0.0) continue;
-                const double x = A[p * ld + k], y = A[q * ld + k];
-                A[p * ld + k] = c * x - s * y;
-                A[q * ld + k] = s * x + c * y;
+            // Z^T <- J^T Z^T (rows p, q; consecutive threads = consecutive columns)
+            for (int pi = zb_i0, k = zb_k0; pi < half;) {
+                const double2 rt = csn[pi];
+                const int2 a = pq[pi];
+                if (a.y >= 0 && rt.y != 0.0) {
+                    double *xp = ZT + a.x * ld + k, *yp = ZT + a.y * ld + k;
+                    const double x = *xp, y = *yp;
+                    *xp = rt.x * x - rt.y * y;
+                    *yp = rt.y * x + rt.x * y;
+                }
+                k += zb_dk; pi += zb_di;
+                if (k >= b) { k -= b; pi++; }
             }
             __syncthreads();
         }

@@ -38,6 +38,26 @@ def hope_oracle():
     return ho
 
 
+@pytest.fixture(scope='session')
+def eval_oracle():
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import eval_oracle as eo
+    return eo
+
+
+def eval_golden(name):
+    """One eval_*.npz golden -> (z, n, CSR (indptr, indices, weights) of the true graph in id order)."""
+    z = np.load(golden_path(name + '.npz'))
+    n = int(z['n'])
+    e = z['edges']
+    src, dst, w = e[:, 0].astype(np.int64), e[:, 1].astype(np.int64), e[:, 2]
+    order = np.lexsort((dst, src))
+    src, dst, w = src[order], dst[order], w[order]
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(indptr, src + 1, 1)
+    return z, n, (np.cumsum(indptr), dst, w)
+
+
 def golden_path(name):
     return os.path.join(GOLDEN, name)
 
