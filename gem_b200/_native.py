@@ -18,6 +18,7 @@ EXPORTS = [
     'gemb_version', 'gemb_last_error', 'gemb_device_count', 'gemb_launch_count', 'gemb_ctx_create', 'gemb_ctx_destroy',
     'gemb_host_alloc', 'gemb_host_free', 'gemb_mem_trim', 'gemb_mem_cached_bytes', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
     'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_apply', 'gemb_hope', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
+    'gemb_recon_create', 'gemb_recon_free', 'gemb_recon_dense', 'gemb_recon_pairs', 'gemb_recon_ranks', 'gemb_recon_top',
 ]
 
 
@@ -89,6 +90,12 @@ def lib():
                                 ctypes.c_int, f64, f64, i32, ctypes.c_int, i64, vp, ctypes.POINTER(N2VStats)]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here = header/library mismatch
+    L.gemb_recon_create.argtypes = [vp, vp, i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    L.gemb_recon_free.argtypes = [vp]
+    L.gemb_recon_dense.argtypes = [vp, vp]
+    L.gemb_recon_pairs.argtypes = [vp, vp, vp, i64, vp]
+    L.gemb_recon_ranks.argtypes = [vp, vp, vp, ctypes.c_int, vp, vp]
+    L.gemb_recon_top.argtypes = [vp, ctypes.c_int, i64, i64, vp, vp, vp, ctypes.POINTER(i64)]
     _lib = L
     return L
 
@@ -274,6 +281,66 @@ class DeviceGraph:
     def free(self):
         if self._h:
             lib().gemb_graph_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Reconstruction:
+    """A_hat = L R^T (zero diagonal) resident on the device: gemb_recon_* (include/gemb200.h)."""
+
+    def __init__(self, ctx, X, split):
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        assert X.ndim == 2
+        self.ctx = ctx
+        self.n, self.d = int(X.shape[0]), int(X.shape[1])
+        self.split = bool(split)
+        self._h = ctypes.c_void_p()
+        check(lib().gemb_recon_create(ctx._h, _ptr(X), self.n, self.d, int(self.split), ctypes.byref(self._h)))
+
+    def dense(self, out=None):
+        A = out if out is not None else np.empty((self.n, self.n), dtype=np.float32)
+        assert A.dtype == np.float32 and A.shape == (self.n, self.n) and A.flags.c_contiguous
+        check(lib().gemb_recon_dense(self._h, _ptr(A)))
+        return A
+
+    def pairs(self, i, j):
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        assert i.shape == j.shape and i.ndim == 1
+        out = np.empty(i.shape[0], dtype=np.float32)
+        check(lib().gemb_recon_pairs(self._h, _ptr(i), _ptr(j), int(i.shape[0]), _ptr(out)))
+        return out
+
+    def ranks(self, indptr, indices, is_undirected):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        assert indptr.shape[0] == self.n + 1
+        rank = np.zeros(max(int(indptr[-1]), 1), dtype=np.int32)
+        n_pred_row = np.zeros(self.n, dtype=np.int32)
+        check(lib().gemb_recon_ranks(self._h, _ptr(indptr), _ptr(indices), int(bool(is_undirected)), _ptr(rank),
+                                     _ptr(n_pred_row)))
+        return rank[:int(indptr[-1])], n_pred_row
+
+    def top(self, is_undirected, max_k=-1):
+        m = ctypes.c_int64(0)
+        check(lib().gemb_recon_top(self._h, int(bool(is_undirected)), int(max_k), 0, None, None, None, ctypes.byref(m)))
+        cnt = int(m.value)
+        i = np.empty(cnt, dtype=np.int32)
+        j = np.empty(cnt, dtype=np.int32)
+        w = np.empty(cnt, dtype=np.float32)
+        if cnt:
+            check(lib().gemb_recon_top(self._h, int(bool(is_undirected)), int(max_k), cnt, _ptr(i), _ptr(j), _ptr(w),
+                                       ctypes.byref(m)))
+        return i, j, w
+
+    def free(self):
+        if self._h:
+            lib().gemb_recon_free(self._h)
             self._h = None
 
     def __del__(self):

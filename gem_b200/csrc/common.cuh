@@ -71,6 +71,8 @@ struct gemb_ctx {
     int rank = 0, nranks = 1;
     void *comm = nullptr;  // ncclComm_t
     int *tile_counter = nullptr;  // device work counter of the persistent SpMM kernel
+    float *spmm_scratch = nullptr;   // chunk partial sums of the heavy rows (n_items x b), grown on demand
+    size_t spmm_scratch_bytes = 0;
     gemb::Timer t_spmm, t_dense, t_comm, t_misc;
 };
 
@@ -79,7 +81,15 @@ struct gemb_csr_dev {
     int32_t *indptr = nullptr;   // n_local + 1
     int32_t *indices = nullptr;  // nnz, global column ids
     float *data = nullptr;       // nnz or nullptr (unit weights)
+    // rows longer than SPMM_HEAVY_DEG (power-law graphs) are cut into chunks of SPMM_HEAVY_CHUNK nonzeros that
+    // whole CTAs process (spmm.cu); built at upload time from the host offsets
+    int32_t n_heavy = 0, n_items = 0;
+    int32_t *heavy_row = nullptr;    // n_heavy: shard-local row ids
+    int32_t *heavy_first = nullptr;  // n_heavy + 1: first chunk of each heavy row
+    int32_t *item_row = nullptr;     // n_items
+    int32_t *item_beg = nullptr;     // n_items: offset of the chunk's first nonzero
 };
+constexpr int SPMM_HEAVY_DEG = 128, SPMM_HEAVY_CHUNK = 512;
 
 struct gemb_graph {
     gemb_ctx *ctx = nullptr;

@@ -227,6 +227,7 @@ int gemb_ctx_destroy(gemb_ctx *c) {
     c->t_comm.destroy();
     c->t_misc.destroy();
     dfree(c->tile_counter);
+    dfree(c->spmm_scratch);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return GEMB_OK;
@@ -295,6 +296,29 @@ static int upload_csr(gemb_ctx *c, int64_t n_local, const int32_t *indptr, const
         GEMB_CUDA(cudaMemcpyAsync(d->data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice,
                                   c->stream));
     }
+    // heavy rows -> chunk work items (see common.cuh); one pass over the host offsets
+    std::vector<int32_t> hrow, hfirst, irow, ibeg;
+    for (int64_t r = 0; r < n_local; r++) {
+        const int32_t s = indptr[r], e = indptr[r + 1];
+        if (e - s <= SPMM_HEAVY_DEG) continue;
+        hrow.push_back((int32_t)r);
+        hfirst.push_back((int32_t)irow.size());
+        for (int32_t b0 = s; b0 < e; b0 += SPMM_HEAVY_CHUNK) { irow.push_back((int32_t)r); ibeg.push_back(b0); }
+    }
+    d->n_heavy = (int32_t)hrow.size();
+    d->n_items = (int32_t)irow.size();
+    if (d->n_heavy) {
+        hfirst.push_back(d->n_items);
+        GEMB_CUDA(dmalloc(&d->heavy_row, sizeof(int32_t) * hrow.size()));
+        GEMB_CUDA(dmalloc(&d->heavy_first, sizeof(int32_t) * hfirst.size()));
+        GEMB_CUDA(dmalloc(&d->item_row, sizeof(int32_t) * irow.size()));
+        GEMB_CUDA(dmalloc(&d->item_beg, sizeof(int32_t) * ibeg.size()));
+        // synchronous copies: the staging vectors die with this scope
+        GEMB_CUDA(cudaMemcpy(d->heavy_row, hrow.data(), sizeof(int32_t) * hrow.size(), cudaMemcpyHostToDevice));
+        GEMB_CUDA(cudaMemcpy(d->heavy_first, hfirst.data(), sizeof(int32_t) * hfirst.size(), cudaMemcpyHostToDevice));
+        GEMB_CUDA(cudaMemcpy(d->item_row, irow.data(), sizeof(int32_t) * irow.size(), cudaMemcpyHostToDevice));
+        GEMB_CUDA(cudaMemcpy(d->item_beg, ibeg.data(), sizeof(int32_t) * ibeg.size(), cudaMemcpyHostToDevice));
+    }
     return GEMB_OK;
 }
 
@@ -355,10 +379,12 @@ int gemb_graph_free(gemb_graph *g) {
         dfree(g->AT.indptr);
         dfree(g->AT.indices);
         dfree(g->AT.data);
+        dfree(g->AT.heavy_row); dfree(g->AT.heavy_first); dfree(g->AT.item_row); dfree(g->AT.item_beg);
     }
     dfree(g->A.indptr);
     dfree(g->A.indices);
     dfree(g->A.data);
+    dfree(g->A.heavy_row); dfree(g->A.heavy_first); dfree(g->A.item_row); dfree(g->A.item_beg);
     delete g;
     return GEMB_OK;
 }

@@ -354,7 +354,12 @@ static int hope_general(HopeWork &W, const Opts &o, int d, float beta, int J, Ho
         GEMB_CUDA(cudaStreamSynchronize(c->stream));
         const double tmax = std::max(theta[b - 1], 1e-300);
         double change = 0.0;
-        for (int j = b - k; j < b; j++) change = std::max(change, fabs(theta[j] - theta_prev[j]) / tmax);
+        // per-value relative change of the SINGULAR values (theta = sigma^2), floored at 1e-3 sigma_max: a change
+        // measured against sigma_max alone never resolves the small end of a skewed spectrum (R-MAT: sigma_k ~ 1e-2 sigma_max)
+        for (int j = b - k; j < b; j++) {
+            const double sj = sqrt(std::max(theta[j], 0.0)), sp = sqrt(std::max(theta_prev[j], 0.0));
+            change = std::max(change, fabs(sj - sp) / std::max(sj, 1e-3 * sqrt(tmax)));
+        }
         R.change = change;
         theta_prev = theta;
         if (o.verbose)
@@ -520,7 +525,10 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         for (int i = 0; i < b; i++) th_sorted[i] = gval[order[i]] * gval[order[i]];
         const double tmax = std::max(th_sorted[0], 1e-300);
         double change = 0.0;
-        for (int j = 0; j < k; j++) change = std::max(change, fabs(th_sorted[j] - th_prev[j]) / tmax);
+        for (int j = 0; j < k; j++) {   // per-value relative change of sigma_j, floored at 1e-3 sigma_max (see hope_general)
+            const double sj = sqrt(th_sorted[j]), sp = sqrt(th_prev[j]);
+            change = std::max(change, fabs(sj - sp) / std::max(sj, 1e-3 * sqrt(tmax)));
+        }
         R.change = change;
         th_prev = th_sorted;
         if (o.verbose)

@@ -30,7 +30,7 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
                      const float *__restrict__ vals, int64_t n_rows, int G, int rows_per_cta,
                      float alpha, float gamma, float delta, const float4 *__restrict__ X,
                      const float4 *__restrict__ Xself, const float4 *__restrict__ X0,
-                     float4 *__restrict__ Y) {
+                     float4 *__restrict__ Y, int heavy_deg) {
     const int tid = threadIdx.x;
     const int lr = tid / G;
     const int c = tid - lr * G;
@@ -38,6 +38,7 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
     const int64_t row = (int64_t)blockIdx.x * rows_per_cta + lr;
     if (row >= n_rows) return;
     const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
+    if (heavy_deg > 0 && e - s > heavy_deg) return;   // a heavy row: spmm_heavy_* kernels below
     const float4 *Xc = X + c;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int i = s;
@@ -80,6 +81,87 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
         r.y = fmaf(delta, z.y, r.y);
         r.z = fmaf(delta, z.z, r.z);
         r.w = fmaf(delta, z.w, r.w);
+    }
+    Y[row * G + c] = r;
+}
+
+// ---- heavy rows (degree > SPMM_HEAVY_DEG; the hubs of a power-law graph -- R-MAT scale 21 has a 61 814-neighbour
+// row, which one 20-thread group would walk for longer than the whole rest of the sweep takes).  Each chunk of
+// SPMM_HEAVY_CHUNK nonzeros is one CTA: its row groups stride over the chunk, the group sums are added in a fixed
+// order in shared memory, and the chunk sum goes to a scratch row; a second tiny kernel adds the chunk sums of a row
+// in chunk order and applies the fused epilogue.  No atomics: the result is bit-reproducible.
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(256)
+spmm_heavy_partial_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                          const float *__restrict__ vals, const int32_t *__restrict__ item_row,
+                          const int32_t *__restrict__ item_beg, int G, int groups, int chunk,
+                          const float4 *__restrict__ X, float4 *__restrict__ partial) {
+    __shared__ float4 red[256];
+    const int tid = threadIdx.x;
+    const int lr = tid / G;
+    const int c = tid - lr * G;
+    const int item = blockIdx.x;
+    const int row = __ldg(item_row + item);
+    const int beg = __ldg(item_beg + item);
+    const int row_end = __ldg(indptr + row + 1);
+    const int end = beg + chunk < row_end ? beg + chunk : row_end;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lr < groups) {
+        const float4 *Xc = X + c;
+        int i = beg + lr;
+        for (; i + 3 * groups < end; i += 4 * groups) {
+            const int c0 = __ldg(indices + i), c1 = __ldg(indices + i + groups);
+            const int c2 = __ldg(indices + i + 2 * groups), c3 = __ldg(indices + i + 3 * groups);
+            float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
+            if (HAS_VAL) {
+                v0 = __ldg(vals + i); v1 = __ldg(vals + i + groups);
+                v2 = __ldg(vals + i + 2 * groups); v3 = __ldg(vals + i + 3 * groups);
+            }
+            const float4 x0 = __ldg(Xc + (int64_t)c0 * G), x1 = __ldg(Xc + (int64_t)c1 * G);
+            const float4 x2 = __ldg(Xc + (int64_t)c2 * G), x3 = __ldg(Xc + (int64_t)c3 * G);
+            fma4(acc, v0, x0); fma4(acc, v1, x1); fma4(acc, v2, x2); fma4(acc, v3, x3);
+        }
+        for (; i < end; i += groups) {
+            const int c0 = __ldg(indices + i);
+            const float v0 = HAS_VAL ? __ldg(vals + i) : 1.f;
+            fma4(acc, v0, __ldg(Xc + (int64_t)c0 * G));
+        }
+        red[tid] = acc;
+    }
+    __syncthreads();
+    if (lr == 0) {
+        float4 sum = red[c];
+        for (int g = 1; g < groups; g++) {
+            const float4 t = red[g * G + c];
+            sum.x += t.x; sum.y += t.y; sum.z += t.z; sum.w += t.w;
+        }
+        partial[(size_t)item * G + c] = sum;
+    }
+}
+
+template <bool HAS_X0, bool HAS_SELF>
+__global__ void __launch_bounds__(256)
+spmm_heavy_finish_kernel(int n_heavy, const int32_t *__restrict__ heavy_row, const int32_t *__restrict__ heavy_first,
+                         int G, float alpha, float gamma, float delta, const float4 *__restrict__ partial,
+                         const float4 *__restrict__ Xself, const float4 *__restrict__ X0, float4 *__restrict__ Y) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = idx / G, c = idx - h * G;
+    if (h >= n_heavy) return;
+    const int64_t row = __ldg(heavy_row + h);
+    const int f = __ldg(heavy_first + h), l = __ldg(heavy_first + h + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = f; it < l; it++) {
+        const float4 t = partial[(size_t)it * G + c];
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+    if (HAS_SELF) {
+        const float4 z = __ldg(Xself + row * G + c);
+        r.x = fmaf(gamma, z.x, r.x); r.y = fmaf(gamma, z.y, r.y); r.z = fmaf(gamma, z.z, r.z); r.w = fmaf(gamma, z.w, r.w);
+    }
+    if (HAS_X0) {
+        const float4 z = __ldg(X0 + row * G + c);
+        r.x = fmaf(delta, z.x, r.x); r.y = fmaf(delta, z.y, r.y); r.z = fmaf(delta, z.z, r.z); r.w = fmaf(delta, z.w, r.w);
     }
     Y[row * G + c] = r;
 }
@@ -207,9 +289,11 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
     dim3 g((unsigned)grid), t(256);
     const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0, *XS4 = (const float4 *)Xself;
     float4 *Y4 = (float4 *)Y;
+    const bool heavy = A.n_items > 0 && G <= 256;
+    const int heavy_deg = heavy ? SPMM_HEAVY_DEG : 0;
 #define LAUNCH(V, Z, S)                                                                              \
     spmm_rowgroup_kernel<V, Z, S><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G,  \
-                                                            rows_per_cta, alpha, gamma, delta, X4, XS4, X04, Y4)
+                                                            rows_per_cta, alpha, gamma, delta, X4, XS4, X04, Y4, heavy_deg)
     const int sel = (A.data ? 4 : 0) | (X0 ? 2 : 0) | (Xself ? 1 : 0);
     switch (sel) {
         case 0: LAUNCH(false, false, false); break;
@@ -224,6 +308,33 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
 #undef LAUNCH
     GEMB_CUDA(cudaGetLastError());
     count_launch();
+    if (heavy) {
+        const size_t need = sizeof(float) * (size_t)A.n_items * b;
+        if (ctx->spmm_scratch_bytes < need) {
+            GEMB_CUDA(dfree(ctx->spmm_scratch));
+            ctx->spmm_scratch = nullptr; ctx->spmm_scratch_bytes = 0;
+            GEMB_CUDA(dmalloc(&ctx->spmm_scratch, need));
+            ctx->spmm_scratch_bytes = need;
+        }
+        float4 *P4 = (float4 *)ctx->spmm_scratch;
+        if (A.data)
+            spmm_heavy_partial_kernel<true><<<A.n_items, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, A.item_row, A.item_beg,
+                                                                               G, rows_per_cta, SPMM_HEAVY_CHUNK, X4, P4);
+        else
+            spmm_heavy_partial_kernel<false><<<A.n_items, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, A.item_row, A.item_beg,
+                                                                                G, rows_per_cta, SPMM_HEAVY_CHUNK, X4, P4);
+        GEMB_CUDA(cudaGetLastError());
+        const int fgrid = (int)(((int64_t)A.n_heavy * G + 255) / 256);
+#define FIN(Z, S) spmm_heavy_finish_kernel<Z, S><<<fgrid, 256, 0, ctx->stream>>>(A.n_heavy, A.heavy_row, A.heavy_first, G, alpha, gamma, \
+                                                                               delta, P4, XS4, X04, Y4)
+        if (X0 && Xself) FIN(true, true);
+        else if (X0) FIN(true, false);
+        else if (Xself) FIN(false, true);
+        else FIN(false, false);
+#undef FIN
+        GEMB_CUDA(cudaGetLastError());
+        count_launch(2);
+    }
     return GEMB_OK;
 }
 

@@ -27,6 +27,8 @@ _OPT_KEYS = ('tol', 'max_iters', 'min_iters', 'oversample', 'katz_terms', 'katz_
 
 class HOPE(StaticGraphEmbedding):
 
+    _recon_split = True      # get_edge_weight form, for the GPU reconstruction (gemb_recon_create)
+
     hyper_params = {
         'method_name': 'hope_gsvd'
     }
@@ -83,8 +85,3 @@ class HOPE(StaticGraphEmbedding):
 
     def get_edge_weight(self, i, j):
         return np.dot(self._X[i, :self._d // 2], self._X[j, self._d // 2:])
-
-    def _reconstruct_block(self):
-        k = self._d // 2
-        X = np.asarray(self._X, dtype=np.float64)
-        return X[:, :k] @ X[:, k:].T

@@ -20,6 +20,8 @@ from gem_b200.embedding.static_graph_embedding import StaticGraphEmbedding
 
 
 class node2vec(StaticGraphEmbedding):
+    _recon_split = False      # get_edge_weight form, for the GPU reconstruction (gemb_recon_create)
+
     hyper_params = {
         'method_name': 'node2vec_rw'
     }
@@ -67,7 +69,3 @@ class node2vec(StaticGraphEmbedding):
 
     def get_edge_weight(self, i, j):
         return np.dot(self._X[i, :], self._X[j, :])
-
-    def _reconstruct_block(self):
-        X = np.asarray(self._X, dtype=np.float64)
-        return X @ X.T

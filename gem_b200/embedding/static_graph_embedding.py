@@ -1,8 +1,10 @@
 """Plugin API of GEM, kept verbatim in behaviour (reference gem/embedding/static_graph_embedding.py:5-83):
 same constructor plumbing (class-level hyper_params dict updated by kwargs, then mirrored into
 self._<key>: SURVEY F13), same getters, same error strings.  get_reconstructed_adj is the one method
-whose n^2 Python loop (reference :59-64) is replaced by the equivalent vectorised product when the
-subclass provides `_reconstruct_block` -- results are identical (diagonal zero, fp64)."""
+whose n^2 Python loop (reference :59-64) is replaced: a subclass that declares `_recon_split` (True: split
+halves, hope.py:43-44; False: dot product, node2vec.py:56-57) gets the product from the GPU
+(gemb_recon_create / gemb_recon_dense, fp32 arithmetic, returned as fp64 with a zero diagonal); there is no
+CPU path for it -- without a GPU it raises RuntimeError."""
 from abc import ABC, abstractmethod
 
 import numpy as np
@@ -40,11 +42,18 @@ class StaticGraphEmbedding(ABC):
             self._X = X
         else:
             node_num = self._node_num
-        block = getattr(self, '_reconstruct_block', None)
-        if block is not None:
-            adj_mtx_r = np.asarray(block(), dtype=np.float64)[:node_num, :node_num].copy()
-            np.fill_diagonal(adj_mtx_r, 0.0)
-            return adj_mtx_r
+        split = getattr(self, '_recon_split', None)
+        if split is not None:
+            from gem_b200 import _native
+            ctx = _native.Context(getattr(self, '_device', 0))
+            try:
+                rec = _native.Reconstruction(ctx, np.asarray(self._X)[:node_num], split)
+                try:
+                    return rec.dense().astype(np.float64)
+                finally:
+                    rec.free()
+            finally:
+                ctx.close()
         adj_mtx_r = np.zeros((node_num, node_num))
         for v_i in range(node_num):
             for v_j in range(node_num):

@@ -110,8 +110,9 @@ typedef struct {
     int32_t oversample;    /* extra block columns, default 16 (block b = min(n, d/2 + oversample)) */
     int32_t max_iters;     /* max subspace iterations, default 30 */
     int32_t min_iters;     /* default 2 */
-    float tol;             /* stop when max_j |theta_j - theta_j_prev| <= tol * theta_max over the top
-                              k Ritz values theta = sigma^2; default 1e-6 */
+    float tol;             /* stop when every one of the top k singular values moved by less than tol relative to
+                              itself between two Rayleigh-Ritz rounds: max_j |sigma_j - sigma_j_prev| /
+                              max(sigma_j, 1e-3 sigma_max) <= tol; default 1e-6 */
     int32_t katz_terms;    /* Horner terms J; 0 = choose so that (beta*||A||_2)^J <= katz_tol */
     float katz_tol;        /* default 1e-7 */
     uint64_t seed;         /* start block, default 1234 */
@@ -189,6 +190,38 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
                   int walk_len, int num_walks, int con_size, int max_iter, double p, double q,
                   int32_t seed, int sequential, int64_t n_rows, float *X_out,
                   gemb_n2v_stats *stats);
+
+/* ---- reconstruction and its evaluation (the step after learn_embedding in tests/fit_model.py:10).
+ * gemb_recon_create replaces the n^2 get_edge_weight calls of static_graph_embedding.py:48-65: A_hat = L R^T with a
+ * zero diagonal, kept ON THE DEVICE (n x n fp32; GEMB_ERR_NOMEM with a message when it does not fit).
+ *   split = 1: L = X[:, :d/2], R = X[:, d/2:]   (HOPE.get_edge_weight, hope.py:43-44)
+ *   split = 0: L = R = X                        (node2vec.get_edge_weight, node2vec.py:56-57)
+ * X: host, n x d row-major fp32. */
+typedef struct gemb_recon gemb_recon;
+int gemb_recon_create(gemb_ctx *ctx, const float *X, int64_t n, int d, int split, gemb_recon **out);
+int gemb_recon_free(gemb_recon *r);
+
+/* The dense matrix get_reconstructed_adj returns (static_graph_embedding.py:48-65): adj_out host, n x n row-major. */
+int gemb_recon_dense(gemb_recon *r, float *adj_out);
+
+/* A_hat[i[t]][j[t]] for m pairs (0 on the diagonal): the sampled-pairs branch of get_edge_list_from_adj_mtrx
+ * (evaluation_util.py:25-28) and the weighted reconstruction error (evaluate_graph_reconstruction.py:37-40). */
+int gemb_recon_pairs(gemb_recon *r, const int32_t *i, const int32_t *j, int64_t m, float *out);
+
+/* computeMAP (metrics.py:28-46) without sorting.  The true graph is a CSR by node id (host, int32).  For every
+ * true edge e = (i -> j): rank_out[e] = 1-based position of (i, j) in node i's predicted edges sorted by weight
+ * (descending, ties in ascending j -- Python's stable sort), or 0 when (i, j) is not a predicted edge (j == i,
+ * A_hat[i][j] <= 0, or j < i with is_undirected -- evaluation_util.py:29-35).  n_pred_row[i] = number of
+ * predicted edges with source i.  AP and MAP follow from the ranks on the host. */
+int gemb_recon_ranks(gemb_recon *r, const int32_t *indptr, const int32_t *indices, int is_undirected,
+                     int32_t *rank_out, int32_t *n_pred_row);
+
+/* computePrecisionCurve (metrics.py:6-25): the predicted edges that can be among the max_k heaviest (max_k < 0: all
+ * of them), i.e. every valid entry >= the max_k-th largest value; UNORDERED.  *m_out = their number.  Call with
+ * cap = 0 to get the count, then with cap >= count and three arrays of that length; the caller orders them
+ * (weight descending, then i, then j ascending = the reference's stable sort of the row-major list). */
+int gemb_recon_top(gemb_recon *r, int is_undirected, int64_t max_k, int64_t cap, int32_t *i_out, int32_t *j_out,
+                   float *w_out, int64_t *m_out);
 
 #ifdef __cplusplus
 }

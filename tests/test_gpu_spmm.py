@@ -54,6 +54,15 @@ def test_spmm_rmat_skewed_and_empty_rows(gpu_ctx):
     assert deg.max() > 50 * max(1, np.median(deg)) and (deg == 0).any()
     _check(gpu_ctx, csr, 80, 0.5, True, False)
     _check(gpu_ctx, csr, 16, 1.0, False, False)
+    # hubs of several thousand neighbours: rows above 128 nonzeros go through the chunked heavy-row kernels
+    # (several 512-nonzero chunks per hub), weighted and unweighted, wide and narrow blocks, A and A^T
+    big = synth.rmat(scale=15, edge_factor=8, seed=4)
+    assert np.diff(big.indptr).max() > 4 * 512
+    _check(gpu_ctx, big, 80, 0.5, True, False)
+    _check(gpu_ctx, big, 8, -1.0, False, True)
+    big.data = np.random.default_rng(9).uniform(0.1, 2.0, big.nnz)
+    _check(gpu_ctx, big, 80, 0.25, True, True)
+    _check(gpu_ctx, big, 144, 1.0, False, False)
 
 
 def test_spmm_linearity_full_size_property(gpu_ctx):

@@ -38,20 +38,18 @@ def test_hyper_params_class_dict_semantics():
         HOPE.hyper_params.update(saved)
 
 
-def test_reconstructed_adj_matches_reference_loop():
+def test_reconstructed_adj_has_no_cpu_path():
+    """get_reconstructed_adj runs on the GPU (tests/test_gpu_recon.py); here: it keeps the reference's side effect
+    (self._X = X, static_graph_embedding.py:56) and fails loudly without a device instead of falling back."""
+    from gem_b200 import _native
     from gem_b200.embedding.hope import HOPE
-    from gem_b200.embedding.node2vec import node2vec
-    rng = np.random.default_rng(0)
-    X = rng.standard_normal((7, 6))
-    for m in (HOPE(d=6, beta=0.1), node2vec(d=6)):
-        A = m.get_reconstructed_adj(X=X)
-        ref = np.zeros((7, 7))
-        for i in range(7):
-            for j in range(7):
-                if i != j:
-                    ref[i, j] = m.get_edge_weight(i, j)       # static_graph_embedding.py:59-64
-        assert np.allclose(A, ref) and np.all(np.diag(A) == 0)
-        assert m.get_embedding() is X                           # reference sets self._X = X (:56)
+    if _native.lib().gemb_device_count() > 0:
+        pytest.skip('a GPU is visible')
+    X = np.random.default_rng(0).standard_normal((7, 6))
+    m = HOPE(d=6, beta=0.1)
+    with pytest.raises(RuntimeError, match='no CUDA device|CUDA'):
+        m.get_reconstructed_adj(X=X)
+    assert m.get_embedding() is X
 
 
 def test_csr_from_networkx_matches_to_numpy_array():
