@@ -14,6 +14,10 @@ the graph.
   N > 1 : launched by torchrun, one rank per GPU; weak scaling: n = N * 1,000,000 (rows per GPU fixed),
           CSR row-sharded, all-gather of the Krylov block per SpMM + b x b all-reduce per Gram (NCCL).
 --workload node2vec: BASELINE.json configs[2] (d=128, p=q=1, 10 walks x 80, context 10, 1 epoch).
+--workload recon: the step after learn_embedding in every reference test (tests/fit_model.py:10):
+  evaluateStaticGraphReconstruction of a HOPE embedding (d=128) of an SBM with --recon-n nodes (default 32768):
+  A_hat = X1 X2^T on the device, rank of every true edge (MAP), precision@1000.  Metric: node PAIRS scored and ranked
+  per second (n^2 / step time; the work is quadratic, so nodes/s would depend on n).
 --impl reference: the reference's CPU implementation of the same path on the host cores
   (HOPE: oracle/hope_oracle.hope_sparse = scipy svds over the matrix-free Katz operator, the only
   form of hope.py:28-36 that fits in memory beyond ~50k nodes; node2vec: the reference's own SNAP
@@ -180,12 +184,48 @@ def cpu_n2v_sample(n_sample, d, walk_len, num_walks, con_size, threads):
     return n_sample / dt, dt, 'port', 1
 
 
+def cpu_recon_sample(n_sample, d, max_k=1000):
+    """The reference's evaluation on the host, vectorised (oracle/eval_oracle.py: one GEMM instead of n^2 np.dot
+    calls, stable argsorts instead of Python sorts -- far faster than gem.evaluation's loops, same results).
+    Returns (pairs/s, seconds)."""
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import eval_oracle as eo
+    from gem_b200 import synth
+    csr = synth.sbm(n=n_sample, block=min(1024, n_sample), seed=42)
+    X = np.random.default_rng(0).standard_normal((n_sample, d)) * 0.3
+    t = time.perf_counter()
+    A = eo.reconstruct(X, True, exact=False)
+    eo.evaluate(A, eo.EdgeSet(csr.n, csr.indptr, csr.indices), is_undirected=True, max_k=max_k)
+    dt = time.perf_counter() - t
+    return float(n_sample) * n_sample / dt, dt
+
+
 # ----------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    if args.workload == 'recon':
+        n_s = args.cpu_sample or 8192
+        secs = []
+        for _ in range(args.warmup):
+            cpu_recon_sample(2048, args.d)
+        for _ in range(args.steps):
+            v, dt = cpu_recon_sample(n_s, args.d)
+            secs.append(dt)
+        value = float(n_s) * n_s * len(secs) / sum(secs)
+        line = {'impl': 'reference', 'metric': 'node pairs evaluated/sec (reconstruction + MAP + precision@1000)', 'value': value,
+                'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': 1e3 * sum(secs) / len(secs), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': 'reconstruction evaluation d=%d, SBM (CPU arm runs a bounded sample)' % args.d},
+                'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': 1, 'kind': 'port', 'host_cores': cores,
+                                 'sample': 'SBM n=%d, random X (d=%d): oracle/eval_oracle.py (vectorised restatement of '
+                                           'gem.evaluation; BLAS GEMM may use several threads)' % (n_s, args.d)},
+                'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line), flush=True)
+        return
     if args.workload == 'hope':
         n_s = args.cpu_sample or 50000
         vals, secs = [], []
@@ -433,13 +473,106 @@ def run_node2vec(args, dist, rank, world, local):
     ctx.close()
 
 
+def run_recon(args, dist, rank, world, local):
+    """SURVEY 8(f) rank 1.  Each rank evaluates its own replica (the path has no exchange step: 'replicas only')."""
+    import ctypes
+    from gem_b200 import _native, synth
+    from gem_b200.embedding.hope import HOPE
+    from gem_b200.evaluation import metrics
+    from gem_b200.evaluation.evaluate_graph_reconstruction import evaluateStaticGraphReconstruction
+    peaks, peak_src = read_peaks()
+    n = args.recon_n
+    csr = synth.sbm(n=n, block=1024 if n % 1024 == 0 else 1000, seed=42)
+    ctx = _native.Context(local)
+    g = _native.DeviceGraph(ctx, csr.n, csr.indptr, csr.indices, None)
+    X, _, _ = g.hope(args.d, args.beta, tol=1e-4, max_iters=40, seed=1234)       # the embedding to evaluate (not timed)
+    g.free()
+    ip32, ix32 = csr.indptr.astype(np.int32), csr.indices.astype(np.int32)
+    lib = _native.lib()
+    K = 1000
+
+    def step():
+        rec = _native.Reconstruction(ctx, X, True)
+        t_sel = time.perf_counter()
+        m = ctypes.c_int64(0)
+        _native.check(lib.gemb_recon_top(rec._h, 1, K, 0, None, None, None, ctypes.byref(m)))   # the counting passes
+        t_sel = time.perf_counter() - t_sel
+        ti, tj, tw = rec.top(True, K)
+        ranks, npr = rec.ranks(ip32, ix32, True)
+        rec.free()
+        return t_sel, ranks
+
+    for _ in range(args.warmup):
+        step()
+    dist_barrier(dist, local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.gemb_launch_count()
+    t0 = time.perf_counter()
+    sel_s = 0.0
+    for _ in range(args.steps):
+        ts, ranks = step()
+        sel_s += ts
+    dist_barrier(dist, local)
+    wall = time.perf_counter() - t0
+    launches = lib.gemb_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    wall = dist_max(dist, wall, local)
+    value = world * float(n) * n * args.steps / wall
+    n_pad = (n + 63) // 64 * 64
+    passes = 32                                            # 1 total count + 31 bisection steps per selection
+    bytes_per_launch = 4.0 * n * n_pad
+    sel_ms = 1e3 * sel_s / (args.steps * passes)
+    achieved = bytes_per_launch / (sel_ms * 1e-3) / 1e9
+    roofline = {'kernel': 'recon_select_kernel<false> (count entries >= T over the n x n reconstruction)', 'bound': 'hbm',
+                'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
+                'traffic': None, 'peak_source': peak_src, 'bytes_per_launch': bytes_per_launch, 'ms_per_launch': sel_ms,
+                'launches_per_step': passes, 'share_of_step': sel_s / max(wall, 1e-9),
+                'note': 'timed on the host clock around the blocking C call that runs the 32 counting passes (each pass = '
+                        'one launch + an 8-byte D2H + stream sync), not with per-kernel events'}
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        HOPE.hyper_params.clear(); HOPE.hyper_params.update({'method_name': 'hope_gsvd'})
+        model = HOPE(d=args.d, beta=args.beta, device=local)
+        evaluateStaticGraphReconstruction(csr, model, X, None, max_k=K)
+        step_ms = []
+        for _ in range(max(3, args.steps)):
+            t1 = time.perf_counter()
+            MAP, prec, _, _ = evaluateStaticGraphReconstruction(csr, model, X, None, max_k=K)
+            step_ms.append((time.perf_counter() - t1) * 1e3)
+        med = float(np.median(step_ms))
+        e2e = {'value': float(n) * n / (med * 1e-3), 'unit': 'pairs/s', 'ms_per_step': med, 'stat': 'median of %d calls' % len(step_ms),
+               'mean_ms_per_step': float(np.mean(step_ms)), 'h2d_bytes_per_step': int(X.nbytes + ip32.nbytes + ix32.nbytes),
+               'd2h_bytes_per_step': int(4 * csr.nnz + 4 * n + 12 * K), 'MAP': MAP, 'precision_at_1000': prec[-1] if prec else None,
+               'call': 'gem_b200.evaluation.evaluate_graph_reconstruction.evaluateStaticGraphReconstruction(csr, model, X, None, max_k=1000)'}
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        n_s = args.cpu_sample or 8192
+        v, dt = cpu_recon_sample(n_s, args.d)
+        cpu = {'value': v, 'unit': 'pairs/s', 'cores': 1, 'kind': 'port', 'host_cores': os.cpu_count(), 'seconds': dt,
+               'sample': 'SBM n=%d, random X (d=%d): oracle/eval_oracle.py, the vectorised restatement of gem.evaluation '
+                         '(BLAS GEMM may use several threads)' % (n_s, args.d)}
+    if rank == 0:
+        line = {'metric': 'node pairs evaluated/sec (reconstruction + MAP + precision@1000)', 'value': value, 'unit': 'pairs/s',
+                'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * wall / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'reconstruction evaluation of a HOPE d=%d embedding, SBM n=%d nnz=%d, undirected, max_k=%d'
+                                       % (args.d, n, csr.nnz, K),
+                           'parallelism': 'single GPU' if world == 1 else 'replicas only (%d independent evaluations)' % world,
+                           'l2_policy': 'inputs larger than L2 (reconstruction %.1f GB vs 126 MB L2)' % (bytes_per_launch / 1e9)},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='hope', choices=['hope', 'node2vec'])
+    ap.add_argument('--workload', default='hope', choices=['hope', 'node2vec', 'recon'])
     ap.add_argument('--n', type=int, default=1_000_000, help='nodes per GPU')
     ap.add_argument('--d', type=int, default=128)
     ap.add_argument('--beta', type=float, default=0.01)
@@ -448,12 +581,13 @@ def main():
     ap.add_argument('--walk-len', type=int, default=80)
     ap.add_argument('--num-walks', type=int, default=10)
     ap.add_argument('--con-size', type=int, default=10)
+    ap.add_argument('--recon-n', type=int, default=32768, help='nodes of the reconstruction workload')
     ap.add_argument('--cpu-sample', type=int, default=None, help='nodes in the CPU baseline sample')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 5 if args.workload == 'hope' else 1
+        args.steps = {'hope': 5, 'recon': 5}.get(args.workload, 1)
     if args.impl == 'reference':
         args.warmup = min(args.warmup, 1)      # each CPU step is a bounded 10-30 s sample
         run_reference(args)
@@ -462,6 +596,8 @@ def main():
     try:
         if args.workload == 'hope':
             run_hope(args, dist, rank, world, local)
+        elif args.workload == 'recon':
+            run_recon(args, dist, rank, world, local)
         else:
             run_node2vec(args, dist, rank, world, local)
     finally:

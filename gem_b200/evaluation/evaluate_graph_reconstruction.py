@@ -19,7 +19,12 @@ from gem_b200.evaluation import metrics
 
 
 def _true_csr(digraph, node_num):
-    """CSR of the true graph by node ID (the reference calls digraph.has_edge(i, j) with matrix positions)."""
+    """CSR of the true graph by node ID (the reference calls digraph.has_edge(i, j) with matrix positions).
+    A gem_b200.graph.HostCSR is taken as it is (rows = node ids), so that graphs too large for networkx can be
+    evaluated."""
+    from gem_b200.graph import HostCSR
+    if isinstance(digraph, HostCSR):
+        return np.asarray(digraph.indptr, dtype=np.int64), np.asarray(digraph.indices, dtype=np.int64)
     e = np.array([(int(u), int(v)) for u, v in digraph.edges()], dtype=np.int64).reshape(-1, 2)
     if e.size and (e.min() < 0 or e.max() >= node_num):
         raise ValueError('node ids must be 0..n-1 (the reference indexes the reconstruction by node id)')
@@ -33,7 +38,8 @@ def _true_csr(digraph, node_num):
 def evaluateStaticGraphReconstruction(digraph, graph_embedding, X_stat, node_l=None, file_suffix=None,
                                       sample_ratio_e=None, is_undirected=True, is_weighted=False, max_k=-1,
                                       device=None):
-    node_num = len(digraph.nodes)
+    from gem_b200.graph import HostCSR
+    node_num = digraph.n if isinstance(digraph, HostCSR) else len(digraph.nodes)
     split = getattr(graph_embedding, '_recon_split', None)
     if split is None:
         raise TypeError('%s does not declare _recon_split (True: hope.py:43-44, False: node2vec.py:56-57)'
@@ -78,12 +84,18 @@ def evaluateStaticGraphReconstruction(digraph, graph_embedding, X_stat, node_l=N
             if is_weighted:
                 # :37-40 -- nx.to_numpy_matrix(digraph) has rows/columns in list(digraph.nodes) order while the
                 # reconstruction is indexed by node id; edge (u -> v) is therefore compared with A_hat[pos u][pos v]
-                pos = np.empty(node_num, dtype=np.int64)
-                pos[np.array([int(u) for u in digraph.nodes], dtype=np.int64)] = np.arange(node_num)
-                ed = [(int(u), int(v), float(wt)) for u, v, wt in digraph.edges(data='weight', default=1)]
-                eu = np.array([t[0] for t in ed], dtype=np.int64)
-                ev = np.array([t[1] for t in ed], dtype=np.int64)
-                a = np.array([t[2] for t in ed], dtype=np.float64)
+                if isinstance(digraph, HostCSR):                  # rows already in id order
+                    pos = np.arange(node_num, dtype=np.int64)
+                    eu = np.repeat(np.arange(node_num, dtype=np.int64), np.diff(indptr))
+                    ev = indices
+                    a = np.ones(ev.size) if digraph.data is None else np.asarray(digraph.data, dtype=np.float64)
+                else:
+                    pos = np.empty(node_num, dtype=np.int64)
+                    pos[np.array([int(u) for u in digraph.nodes], dtype=np.int64)] = np.arange(node_num)
+                    ed = [(int(u), int(v), float(wt)) for u, v, wt in digraph.edges(data='weight', default=1)]
+                    eu = np.array([t[0] for t in ed], dtype=np.int64)
+                    ev = np.array([t[1] for t in ed], dtype=np.int64)
+                    a = np.array([t[2] for t in ed], dtype=np.float64)
                 est = rec.pairs(pos[eu], pos[ev]).astype(np.float64)
                 nz = a != 0
                 err = float(np.sqrt(np.sum((a[nz] - est[nz]) ** 2)))

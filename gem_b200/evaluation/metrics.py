@@ -15,25 +15,24 @@ def map_from_ranks(n, indptr, ranks, is_undirected, out_degree=None):
     -> (MAP, node_ap, count)"""
     indptr = np.asarray(indptr, dtype=np.int64)
     ranks = np.asarray(ranks, dtype=np.int64)
-    node_ap = [0.0] * n
     outdeg = np.diff(indptr) if out_degree is None else np.asarray(out_degree)
-    count = 0
-    for v in range(n):
-        if not is_undirected and outdeg[v] == 0:
-            continue
-        count += 1
-        r = ranks[indptr[v]:indptr[v + 1]]
-        r = np.sort(r[r > 0])
-        if r.size == 0:
-            continue
-        acc = 0.0
-        for t, rk in enumerate(r.tolist(), 1):               # python sum(): sequential fp64
-            acc += (1.0 * t / rk) * 1.0
-        node_ap[v] = float(acc / float(r.size))
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    hit = ranks > 0
+    hr, rk = rows[hit], ranks[hit]
+    order = np.lexsort((rk, hr))                              # by node, then by rank
+    hr, rk = hr[order], rk[order]
+    hits = np.bincount(hr, minlength=n)                       # sum(delta_factors) per node
+    first = np.cumsum(hits) - hits
+    t = np.arange(1, hr.size + 1, dtype=np.int64) - first[hr]  # number of hits up to and including this one
+    # np.bincount adds its weights one by one in input order = rank order: the reference's sequential sum()
+    sums = np.bincount(hr, weights=t.astype(np.float64) / rk.astype(np.float64), minlength=n)
+    node_ap = np.where(hits > 0, sums / np.maximum(hits, 1), 0.0)
+    counted = np.ones(n, dtype=bool) if is_undirected else (outdeg > 0)
+    count = int(counted.sum())
     total = 0.0
-    for a in node_ap:
+    for a in node_ap[counted].tolist():                       # sum(node_ap): sequential, in node order
         total += a
-    return (total / count if count else float('nan')), np.array(node_ap), count
+    return (total / count if count else float('nan')), node_ap, count
 
 
 def precision_curve_from_top(i, j, w, has_edge, max_k=-1):
