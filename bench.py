@@ -317,6 +317,15 @@ def run_hope(args, dist, rank, world, local):
     wall_s = dist_max(dist, wall_s, local)
     value = n * args.steps / (dev_ms * 1e-3)
 
+    # accuracy of the timed solution, outside the timed region: one more identical solve that also applies the fp32
+    # Katz operator to the result, || S^T u_j - sigma_j v_j || / sigma_max over the k triplets (collective on N > 1)
+    resid_max = None
+    try:
+        _, _, st_r = g.hope(args.d, args.beta, want_output=False, compute_residual=1, **solver)
+        resid_max = float(st_r['resid_max'])
+    except Exception as exc:                                   # diagnostics only: never fail the bench line
+        resid_max = 'unavailable: %s' % exc
+
     # roofline of the dominant kernel (CSR SpMM): algorithmic bytes per launch / mean launch time
     spmm_ms_per = stats['spmm_ms'] / max(stats['spmm_count'], 1)
     achieved = stats['spmm_bytes'] / (spmm_ms_per * 1e-3) / 1e9 if spmm_ms_per > 0 else 0.0
@@ -380,7 +389,7 @@ def run_hope(args, dist, rank, world, local):
                                        'deg 16 in / 4 out, seed 42' % (args.d, args.beta, n, args.n, csr.nnz),
                            'solver': dict(solver, block=stats['block'], katz_terms=stats['katz_terms'],
                                           iters=stats['iters'], converged=stats['converged'],
-                                          ritz_change=stats['ritz_change'],
+                                          ritz_change=stats['ritz_change'], resid_max_rel_sigma_max=resid_max,
                                           algorithm={1: 'subspace iteration on S^T S (Katz sweeps)',
                                                      2: 'Chebyshev-filtered subspace iteration on A (S = f(A), A symmetric)'}
                                           .get(stats['algorithm'], stats['algorithm'])),
