@@ -18,6 +18,7 @@ EXPORTS = [
     'gemb_version', 'gemb_last_error', 'gemb_device_count', 'gemb_launch_count', 'gemb_ctx_create', 'gemb_ctx_destroy',
     'gemb_host_alloc', 'gemb_host_free', 'gemb_mem_trim', 'gemb_mem_cached_bytes', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
     'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_apply', 'gemb_hope', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
+    'gemb_edge_list_scan', 'gemb_edge_list_parse', 'gemb_edge_list_write', 'gemb_emb_read', 'gemb_emb_write',
     'gemb_recon_create', 'gemb_recon_free', 'gemb_recon_dense', 'gemb_recon_pairs', 'gemb_recon_ranks', 'gemb_recon_top',
 ]
 
@@ -90,6 +91,12 @@ def lib():
                                 ctypes.c_int, f64, f64, i32, ctypes.c_int, i64, vp, ctypes.POINTER(N2VStats)]
     for name in EXPORTS:
         getattr(L, name)  # AttributeError here = header/library mismatch
+    cp = ctypes.c_char_p
+    L.gemb_edge_list_scan.argtypes = [cp, i64, ctypes.POINTER(i64)]
+    L.gemb_edge_list_parse.argtypes = [cp, i64, i64, vp, vp, vp, ctypes.POINTER(i32)]
+    L.gemb_edge_list_write.argtypes = [cp, i64, vp, vp, vp, i64]
+    L.gemb_emb_read.argtypes = [cp, ctypes.POINTER(i64), ctypes.POINTER(i32), vp]
+    L.gemb_emb_write.argtypes = [cp, i64, vp, i32, vp, i64]
     L.gemb_recon_create.argtypes = [vp, vp, i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     L.gemb_recon_free.argtypes = [vp]
     L.gemb_recon_dense.argtypes = [vp, vp]

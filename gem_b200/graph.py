@@ -66,9 +66,15 @@ def from_edges(n, src, dst, w=None, nodes=None, unit_if_all_ones=True):
     dst = np.asarray(dst, dtype=np.int64)
     if src.size and (src.min() < 0 or dst.min() < 0 or src.max() >= n or dst.max() >= n):
         raise ValueError('edge endpoint outside [0, n)')
-    order = np.lexsort((dst, src))
-    s, t = src[order], dst[order]
-    ww = None if w is None else np.asarray(w, dtype=np.float64)[order]
+    ww = None if w is None else np.asarray(w, dtype=np.float64)
+    key = src * np.int64(n) + dst if n < (1 << 31) else None
+    if key is not None and (key.size < 2 or bool(np.all(key[1:] >= key[:-1]))):
+        s, t = src, dst                                        # already in row-major order (files we wrote ourselves)
+    else:
+        # stable: among equal (src, dst) the input order survives, so "last wins" below is the LAST line of a file
+        order = np.argsort(key, kind='stable') if key is not None else np.lexsort((dst, src))
+        s, t = src[order], dst[order]
+        ww = None if ww is None else ww[order]
     if s.size > 1:
         dup = (s[1:] == s[:-1]) & (t[1:] == t[:-1])
         if dup.any():

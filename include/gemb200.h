@@ -223,6 +223,25 @@ int gemb_recon_ranks(gemb_recon *r, const int32_t *indptr, const int32_t *indice
 int gemb_recon_top(gemb_recon *r, int is_undirected, int64_t max_k, int64_t cap, int32_t *i_out, int32_t *j_out,
                    float *w_out, int64_t *m_out);
 
+/* ---- wire formats: the reference's text files, read and written natively and in parallel.
+ * HOST code only -- these entry points need no GPU.
+ * Edge list: every non-blank line "src dst [weight]" (loadGraphFromEdgeListTxt, graph_util.py:143-158: exactly three
+ * tokens -> float(weight), otherwise 1.0).  `skip` leading lines are ignored (the two header lines that
+ * saveGraphToEdgeListTxt writes, graph_util.py:131-132).  scan counts the edge lines; parse fills caller arrays of
+ * that length (w may be NULL); *all_unit = 1 when no weight differs from 1.0. */
+int gemb_edge_list_scan(const char *path, int64_t skip, int64_t *n_edges);
+int gemb_edge_list_parse(const char *path, int64_t skip, int64_t n_edges, int64_t *src, int64_t *dst, double *w,
+                         int32_t *all_unit);
+/* One "%d %d %f\n" per edge (saveGraphToEdgeListTxtn2v, graph_util.py:137-140); header_nodes >= 0 first writes
+ * "<nodes>\n<edges>\n" (saveGraphToEdgeListTxt, :129-134).  w == NULL writes 1.000000. */
+int gemb_edge_list_write(const char *path, int64_t n_edges, const int64_t *src, const int64_t *dst, const double *w,
+                         int64_t header_nodes);
+/* ".emb": "<rows> <d>" then "<id> v1 ... vd" (loadEmbedding, graph_util.py:161-169; written by SNAP's WriteOutput,
+ * bin@0x406ef0, with 6 significant digits).  read: X == NULL returns only rows and d; otherwise X is rows x d fp64,
+ * zeroed by the caller, row = id.  write: ids == NULL means rows 0..n_ids-1; X is indexed by id. */
+int gemb_emb_read(const char *path, int64_t *rows, int32_t *d, double *X);
+int gemb_emb_write(const char *path, int64_t n_ids, const int64_t *ids, int32_t d, const double *X, int64_t header_rows);
+
 #ifdef __cplusplus
 }
 #endif

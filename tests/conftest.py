@@ -2,6 +2,11 @@ import os
 import subprocess
 import sys
 
+# BLAS / OpenMP pools of 64+ threads per process (and two such processes in the gloo tests) thrash on a shared or
+# CPU-limited box: the CPU suite went from 30 s to 5 minutes under load.  Nothing here needs more than a few threads.
+for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+    os.environ.setdefault(_v, '4')
+
 import numpy as np
 import pytest
 
