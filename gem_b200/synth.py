@@ -46,7 +46,11 @@ def sbm(n=1_000_000, block=1000, deg_in=16.0, deg_out=4.0, seed=42):
     return _csr_from_pairs(n, np.concatenate((u, uo)), np.concatenate((v, vo)))
 
 
-def rmat(scale=24, edge_factor=8, a=0.57, b=0.19, c=0.19, seed=42, chunk=1 << 24):
+def rmat(scale=24, edge_factor=8, a=0.57, b=0.19, c=0.19, seed=42, chunk=1 << 24, permute=True):
+    """Graph500 R-MAT: edge_factor * 2^scale undirected pairs, symmetrised, self-loops and
+    duplicates removed, unit weights.  permute=True relabels the vertices with a random permutation as the Graph500
+    generator does: without it the hubs are the lowest ids, and contiguous equal-row shards (multi-GPU) would put most
+    of the edges on rank 0."""
     rng = np.random.default_rng(seed)
     n = 1 << scale
     m = n * edge_factor
@@ -64,4 +68,8 @@ def rmat(scale=24, edge_factor=8, a=0.57, b=0.19, c=0.19, seed=42, chunk=1 << 24
             v = (v << 1) | vbit
         us.append(u)
         vs.append(v)
-    return _csr_from_pairs(n, np.concatenate(us), np.concatenate(vs))
+    u, v = np.concatenate(us), np.concatenate(vs)
+    if permute:
+        perm = rng.permutation(n)
+        u, v = perm[u], perm[v]
+    return _csr_from_pairs(n, u, v)
