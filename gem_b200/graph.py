@@ -103,24 +103,57 @@ def from_scipy(A):
 
 def from_networkx(graph, by_label=False):
     """by_label=False (HOPE): row r <-> list(graph.nodes)[r]  (hope.py:28 / SURVEY F6).
-    by_label=True (node2vec): row = integer node label, n = max label + 1 (graph_util.py:168)."""
+    by_label=True (node2vec): row = integer node label, n = max label + 1 (graph_util.py:168).
+    An undirected nx.Graph gives both directions, as nx.to_numpy_matrix does.  Integer-labelled graphs take a
+    vectorised path (one np.fromiter over graph.edges, 2x the speed of the per-edge loop); anything else -- string
+    labels, non-numeric weights -- falls back to the loop."""
+    import itertools
+    import operator
     nodes = list(graph.nodes)
+    m = graph.number_of_edges()
+    src = dst = w = None
+    undirected_done = False
+    lab = np.asarray(nodes) if nodes else np.zeros(0, np.int64)
+    adj = getattr(graph, '_adj', None)
+    if m and lab.ndim == 1 and lab.dtype.kind in 'iu' and isinstance(adj, dict) and not graph.is_multigraph():
+        try:
+            # dict-of-dict-of-dict walked at C speed: keys of the inner dicts = neighbours, in graph.edges order
+            deg = np.fromiter(map(len, adj.values()), dtype=np.int64, count=len(adj))
+            tot = int(deg.sum())
+            v = np.fromiter(itertools.chain.from_iterable(adj.values()), dtype=np.int64, count=tot)
+            w = np.fromiter(map(operator.methodcaller('get', 'weight', 1),
+                                itertools.chain.from_iterable(map(dict.values, adj.values()))),
+                            dtype=np.float64, count=tot)
+            u = np.repeat(np.fromiter(adj.keys(), dtype=np.int64, count=len(adj)), deg)
+            if by_label:
+                src, dst = u, v
+            elif np.array_equal(lab, np.arange(lab.size)):
+                src, dst = u, v                                # labels are already the row numbers
+            else:
+                order = np.argsort(lab, kind='stable')
+                sl = lab[order].astype(np.int64)
+                src, dst = order[np.searchsorted(sl, u)], order[np.searchsorted(sl, v)]
+            undirected_done = True                             # an nx.Graph stores both directions in _adj
+        except (TypeError, ValueError, AttributeError):
+            src = None
+    if src is None:
+        index = None if by_label else {u: i for i, u in enumerate(nodes)}
+        s_l, d_l, w_l = [], [], []
+        for u, v, ww in graph.edges(data='weight', default=1):
+            if by_label:
+                s_l.append(int(u)); d_l.append(int(v))
+            else:
+                s_l.append(index[u]); d_l.append(index[v])
+            w_l.append(float(ww))
+        src, dst, w = np.array(s_l, dtype=np.int64), np.array(d_l, dtype=np.int64), np.array(w_l, dtype=np.float64)
     if by_label:
-        labels = np.array([int(x) for x in nodes], dtype=np.int64) if nodes else np.zeros(0, np.int64)
-        n = int(labels.max()) + 1 if labels.size else 0
-        index = None
+        n = int(np.asarray([int(x) for x in nodes], dtype=np.int64).max()) + 1 if nodes else 0
     else:
         n = len(nodes)
-        index = {u: i for i, u in enumerate(nodes)}
-    src, dst, w = [], [], []
-    for u, v, ww in graph.edges(data='weight', default=1):
-        if by_label:
-            src.append(int(u)); dst.append(int(v))
-        else:
-            src.append(index[u]); dst.append(index[v])
-        w.append(float(ww))
-    return from_edges(n, np.array(src, dtype=np.int64), np.array(dst, dtype=np.int64),
-                      np.array(w, dtype=np.float64), nodes=nodes)
+    if not graph.is_directed() and not undirected_done:
+        off = src != dst
+        src, dst, w = np.concatenate((src, dst[off])), np.concatenate((dst, src[off])), np.concatenate((w, w[off]))
+    return from_edges(n, src, dst, w, nodes=nodes)
 
 
 def n2v_inputs_from_networkx(graph):

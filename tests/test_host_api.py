@@ -95,3 +95,45 @@ def test_wire_formats_roundtrip(tmp_path):
     e = str(tmp_path / 'x.emb')
     graph_util.saveEmbedding(X, e, ids=[2, 0, 3, 1])
     assert np.allclose(graph_util.loadEmbedding(e), X, rtol=1e-5)
+
+
+def test_from_networkx_fast_and_fallback_paths_match_to_numpy_array():
+    """Integer-labelled graphs take the vectorised adjacency walk, everything else the per-edge loop; both must equal
+    nx.to_numpy_array(graph, nodelist=list(graph.nodes)) (= the reference's nx.to_numpy_matrix, hope.py:28),
+    including undirected graphs (both directions), self loops, missing weights and shifted / unordered labels."""
+    import networkx as nx
+    from gem_b200 import graph as hg
+    rng = np.random.default_rng(0)
+
+    def check(G, by_label=False):
+        c = hg.from_networkx(G, by_label=by_label)
+        if by_label:
+            n = max(G.nodes) + 1
+            dense = np.zeros((n, n))
+            for u, v, w in G.edges(data='weight', default=1):
+                dense[u, v] = w
+                if not G.is_directed():
+                    dense[v, u] = w
+        else:
+            dense = nx.to_numpy_array(G, nodelist=list(G.nodes))
+            assert c.nodes == list(G.nodes)
+        assert np.array_equal(c.to_scipy().toarray(), dense)
+
+    G = nx.DiGraph()
+    for _ in range(500):
+        u, v = (int(x) for x in rng.integers(0, 60, 2))
+        G.add_edge(u * 3 + 5, v * 3 + 5, weight=float(rng.uniform(0.1, 2)))
+    G.add_edge(7, 8)                                          # no weight attribute -> 1
+    check(G); check(G, True)
+    H = nx.Graph()
+    for _ in range(300):
+        u, v = (int(x) for x in rng.integers(0, 50, 2))
+        H.add_edge(u, v, weight=float(rng.integers(1, 4)))
+    H.add_edge(3, 3)
+    check(H); check(H, True)
+    S = nx.DiGraph(); S.add_edge('a', 'b', weight=2.0); S.add_edge('b', 'c')
+    check(S)
+    U = nx.Graph(); U.add_edge('x', 'y'); U.add_edge('y', 'y')
+    check(U)
+    E = nx.DiGraph(); E.add_nodes_from([0, 1, 2])
+    check(E)
