@@ -160,6 +160,20 @@ def n2v_inputs_from_networkx(graph):
     """What the SNAP binary would see after GEM wrote the edge list (node2vec.py:34, graph_util.py:137-140):
     CSR by integer label with weights rounded through '%f', and the node table in first-appearance
     order of the edge list (SNAP ReadGraph)."""
+    import itertools
+    import operator
+    adj = getattr(graph, '_adj', None)
+    if graph.is_directed() and isinstance(adj, dict) and not graph.is_multigraph() and graph.number_of_edges():
+        try:   # the adjacency dicts walked at C speed, in graph.edges order (see from_networkx)
+            deg = np.fromiter(map(len, adj.values()), dtype=np.int64, count=len(adj))
+            tot = int(deg.sum())
+            dst = np.fromiter(itertools.chain.from_iterable(adj.values()), dtype=np.int64, count=tot)
+            w = np.fromiter(map(operator.methodcaller('get', 'weight', 1),
+                                itertools.chain.from_iterable(map(dict.values, adj.values()))), dtype=np.float64, count=tot)
+            src = np.repeat(np.fromiter(adj.keys(), dtype=np.int64, count=len(adj)), deg)
+            return n2v_inputs_from_edges(src, dst, w)
+        except (TypeError, ValueError, AttributeError):
+            pass
     src, dst, w = [], [], []
     for u, v, ww in graph.edges(data='weight', default=1):
         src.append(int(u)); dst.append(int(v)); w.append(float(ww))
