@@ -26,7 +26,10 @@ k = a.d // 2
 b = k + 16
 f = lambda l: beta * l / (1.0 - beta * l)
 print('n', n, 'nnz', A.nnz, 'rho %.4g beta %.4g' % (rho, beta))
-ex = np.linalg.eigvalsh(A.astype(np.float64).toarray()) if n <= 8192 else sla.eigsh(A.astype(np.float64), k=min(n - 2, 4 * k), which='BE', return_eigenvectors=False)
+if n <= 8192:
+    ex = np.linalg.eigvalsh(A.astype(np.float64).toarray())
+else:
+    ex = sla.eigsh(A.astype(np.float64), k=k + 4, which='LA', tol=1e-9, ncv=4 * k, return_eigenvectors=False)
 exact = np.sort(np.abs(f(ex)))[::-1][:k]
 
 
@@ -127,7 +130,8 @@ def solve(mode):
     return a.max_iters, sweeps, err
 
 
-for mode in ('guard', 'bcgs', 'bcgs+lock'):
+import os
+for mode in os.environ.get('MODES', 'guard,bcgs,bcgs+lock').split(','):
     t = time.time()
     it, sw, err = solve(mode)
     print('%s: %d rounds, %d sweeps, max rel sigma error %.3g  (%.1f s)' % (mode, it, sw, err, time.time() - t), flush=True)

@@ -137,3 +137,31 @@ def test_from_networkx_fast_and_fallback_paths_match_to_numpy_array():
     check(U)
     E = nx.DiGraph(); E.add_nodes_from([0, 1, 2])
     check(E)
+
+
+def test_synthetic_generators_match_the_survey_configs():
+    """SURVEY 8(d): SBM with ~16 intra + ~4 inter neighbours per node, symmetric, no loops, deterministic in the seed;
+    Graph500 R-MAT symmetrised, deduplicated, hubs and isolated nodes, vertex labels permuted so that contiguous
+    equal-row shards carry similar numbers of edges."""
+    from gem_b200 import synth
+    a = synth.sbm(n=20_000, block=1000, seed=42)
+    b = synth.sbm(n=20_000, block=1000, seed=42)
+    assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and a.data is None
+    assert a.is_symmetric() and abs(a.nnz / a.n - 20.0) < 0.3
+    rows = np.repeat(np.arange(a.n), np.diff(a.indptr))
+    assert not np.any(rows == a.indices)                                     # no self loops
+    intra = (rows // 1000) == (a.indices // 1000)
+    assert abs(intra.mean() - 0.8) < 0.02                                    # 16 of 20 neighbours inside the block
+    t = a.transpose()
+    assert np.array_equal(t.indptr, a.indptr) and np.array_equal(t.indices, a.indices)
+    r = synth.rmat(scale=13, edge_factor=8, seed=42)
+    assert r.n == 8192 and r.is_symmetric() and r.nnz <= 2 * 8 * 8192
+    deg = np.diff(r.indptr)
+    assert deg.max() > 100 * max(1.0, np.median(deg)) and (deg == 0).sum() > 0.2 * r.n
+    per = r.n // 8
+    shard_nnz = np.array([r.indptr[(p + 1) * per] - r.indptr[p * per] for p in range(8)])
+    assert shard_nnz.max() < 1.6 * shard_nnz.mean()                          # permuted labels: balanced shards
+    u = synth.rmat(scale=13, edge_factor=8, seed=42, permute=False)
+    per_u = np.array([u.indptr[(p + 1) * per] - u.indptr[p * per] for p in range(8)])
+    assert per_u.max() > 2.0 * per_u.mean()                                  # without it rank 0 owns the hubs
+    assert np.array_equal(np.sort(np.diff(u.indptr)), np.sort(deg))          # same graph up to relabelling
