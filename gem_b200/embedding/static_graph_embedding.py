@@ -11,61 +11,64 @@ import numpy as np
 
 
 class StaticGraphEmbedding(ABC):
+    """Base of the drop-in embedding classes.  Subclasses provide a class-level `hyper_params` dict (at least
+    'method_name'), `learn_embedding` and `get_edge_weight`; a subclass whose score is one of the two reference forms
+    declares `_recon_split` so that reconstruction and evaluation run on the GPU."""
 
-    def __init__(self, *args, **kwargs):
-        """Initialize the Embedding class"""
-        self._method_name = None
-        self._d = None
-        self._X = None
-        self.hyper_params.update(kwargs)
-        for key in self.hyper_params.keys():
-            self.__setattr__('_%s' % key, self.hyper_params[key])
-        for dictionary in args:
-            for key in dictionary:
-                self.__setattr__('_%s' % key, dictionary[key])
+    def __init__(self, *param_dicts, **params):
+        self._method_name = self._d = self._X = None
+        # SURVEY F13, kept on purpose: keyword arguments are merged into the dict shared by the CLASS (later instances
+        # inherit them); every entry then becomes an attribute with a leading underscore.  Positional dicts are
+        # applied last, override, and do not touch the shared dict.
+        shared = self.hyper_params
+        shared.update(params)
+        settings = dict(shared)
+        for extra in param_dicts:
+            settings.update(extra)
+        for name, value in settings.items():
+            setattr(self, '_' + name, value)
 
-    def get_method_name(self):
-        return self._method_name
-
-    def get_method_summary(self):
-        return '%s_%d' % (self._method_name, self._d)
-
+    # -- getters (same strings and errors as the reference, :21-46)
     def get_embedding(self):
         if self._X is None:
             raise ValueError("Embedding not learned yet")
         return self._X
 
+    def get_method_name(self):
+        return self._method_name
+
+    def get_method_summary(self):
+        return '{}_{:d}'.format(self._method_name, self._d)
+
     def get_reconstructed_adj(self, X=None, node_l=None):
-        """Reference :48-65: sets self._X when X is given; A_hat[i, j] = get_edge_weight(i, j), i != j."""
-        if X is not None:
-            node_num = X.shape[0]
-            self._X = X
+        """A_hat[i, j] = get_edge_weight(i, j) off the diagonal, 0 on it (reference :48-65).  As there, a given X
+        replaces the stored embedding and `node_l` is accepted but unused."""
+        if X is None:
+            rows = self._node_num
         else:
-            node_num = self._node_num
+            self._X = X
+            rows = X.shape[0]
         split = getattr(self, '_recon_split', None)
-        if split is not None:
-            from gem_b200 import _native
-            ctx = _native.Context(getattr(self, '_device', 0))
+        if split is None:
+            # a subclass with a score function of its own: evaluate it entry by entry, like the reference
+            score = self.get_edge_weight
+            return np.array([[0.0 if i == j else score(i, j) for j in range(rows)] for i in range(rows)],
+                            dtype=np.float64).reshape(rows, rows)
+        from gem_b200 import _native
+        ctx = _native.Context(getattr(self, '_device', 0))
+        try:
+            rec = _native.Reconstruction(ctx, np.asarray(self._X)[:rows], split)
             try:
-                rec = _native.Reconstruction(ctx, np.asarray(self._X)[:node_num], split)
-                try:
-                    return rec.dense().astype(np.float64)
-                finally:
-                    rec.free()
+                return rec.dense().astype(np.float64)
             finally:
-                ctx.close()
-        adj_mtx_r = np.zeros((node_num, node_num))
-        for v_i in range(node_num):
-            for v_j in range(node_num):
-                if v_i == v_j:
-                    continue
-                adj_mtx_r[v_i, v_j] = self.get_edge_weight(v_i, v_j)
-        return adj_mtx_r
+                rec.free()
+        finally:
+            ctx.close()
 
     @abstractmethod
     def learn_embedding(self, graph):
-        """Learn the graph embedding from a networkx DiGraph."""
+        """graph: networkx DiGraph (or the CSR forms the subclass documents) -> n x d ndarray, also stored."""
 
     @abstractmethod
     def get_edge_weight(self, i, j):
-        """Weight of the edge between rows i and j of the embedding."""
+        """Score of the edge i -> j from rows i and j of the embedding."""
