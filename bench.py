@@ -226,8 +226,15 @@ def run_reference(args):
                 'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         print(json.dumps(line), flush=True)
         return
+    # bounded CPU work: about 150 s of timed samples in total whatever --steps is (a 50k-node HOPE sample takes ~40 s,
+    # a 4000-node node2vec sample ~65 s on the 128-core box; both scale about linearly in the sample size)
+    def bounded(base_nodes, base_seconds, floor):
+        if args.cpu_sample:
+            return args.cpu_sample
+        return max(floor, int(base_nodes * min(1.0, 150.0 / (max(args.steps, 1) * base_seconds))))
+
     if args.workload == 'hope':
-        n_s = args.cpu_sample or 50000
+        n_s = bounded(50000, 40.0, 8000) // 1000 * 1000
         vals, secs = [], []
         for _ in range(args.warmup):
             cpu_hope_sample(n_s, args.d, args.beta, HOPE_SOLVER['tol'])
@@ -240,9 +247,10 @@ def run_reference(args):
                   'Katz operator, J=%d Horner terms' % (n_s, args.d, args.beta, HOPE_SOLVER['tol'], info['katz_terms']))
         cfg = {'workload': 'HOPE d=%d beta=%g, SBM 1M nodes / 20M edges (CPU arm runs a bounded sample)' % (args.d, args.beta)}
     else:
-        n_s = args.cpu_sample or 4000
+        n_s = bounded(4000, 65.0, 500)
+        n_s = n_s // 1000 * 1000 if n_s >= 1000 else n_s // 100 * 100      # synth.sbm wants whole blocks
         for _ in range(args.warmup):
-            cpu_n2v_sample(1000, args.d, args.walk_len, args.num_walks, args.con_size, cores)
+            cpu_n2v_sample(min(1000, n_s), args.d, args.walk_len, args.num_walks, args.con_size, cores)
         secs = []
         for _ in range(args.steps):
             v, dt, kind, used = cpu_n2v_sample(n_s, args.d, args.walk_len, args.num_walks, args.con_size, cores)
