@@ -16,17 +16,22 @@ ap.add_argument('--max-iters', type=int, default=60)
 ap.add_argument('--deg', type=int, default=8)
 ap.add_argument('--group', type=int, default=16)
 ap.add_argument('--sbm', type=int, default=0)
+ap.add_argument('--oversample', type=int, default=16)
+ap.add_argument('--warm', type=int, default=3)
+ap.add_argument('--no-exact', action='store_true')
 a = ap.parse_args()
 csr = synth.sbm(n=a.sbm, block=1000) if a.sbm else synth.rmat(scale=a.scale)
 A = csr.to_scipy().astype(np.float32)
 n = A.shape[0]
-rho = float(sla.eigsh(A.astype(np.float64), k=1, which='LA', return_eigenvectors=False)[0])
+rho = 1.0 if a.sbm else float(sla.eigsh(A.astype(np.float64), k=1, which='LA', return_eigenvectors=False)[0])
 beta = 0.01 if a.sbm else 0.5 / rho
 k = a.d // 2
-b = k + 16
+b = k + a.oversample
 f = lambda l: beta * l / (1.0 - beta * l)
 print('n', n, 'nnz', A.nnz, 'rho %.4g beta %.4g' % (rho, beta))
-if n <= 8192:
+if a.no_exact:
+    ex = np.ones(k + 4)
+elif n <= 8192:
     ex = np.linalg.eigvalsh(A.astype(np.float64).toarray())
 else:
     ex = sla.eigsh(A.astype(np.float64), k=k + 4, which='LA', tol=1e-9, ncv=4 * k, return_eigenvectors=False)
@@ -68,7 +73,7 @@ def solve(mode):
     rng = np.random.default_rng(1234)
     V = cholqr2(rng.standard_normal((n, b)).astype(np.float32))
     sweeps = 0
-    for _ in range(3):
+    for _ in range(a.warm):
         V = cholqr2(A @ V); sweeps += 1
     Q = np.zeros((n, 0), dtype=np.float32); lamQ = np.zeros(0)
     sig_prev = np.zeros(k)
@@ -85,8 +90,18 @@ def solve(mode):
         change = np.max(np.abs(sig - sig_prev) / np.maximum(sig, 1e-3 * sig[0]))
         err = np.max(np.abs(sig - exact) / exact)
         sig_prev = sig
-        print('  %s it %d change %.3g  err vs exact %.3g  locked %d sweeps %d' % (mode, it, change, err, Q.shape[1], sweeps), flush=True)
+        kk = k - Q.shape[1]
+        Zt_ = Z[:, order[:kk]].astype(np.float32)
+        lt_ = lam[order[:kk]]
+        ra_ = np.linalg.norm(W @ Zt_ - (V @ Zt_) * lt_[None, :].astype(np.float32), axis=0)
+        resid = float(np.max(beta / (1.0 - beta * lt_) ** 2 * ra_) / sig[0])
+        print('  %s it %d change %.3g  resid %.3g  locked %d sweeps %d' % (mode, it, change, resid, Q.shape[1], sweeps), flush=True)
         if it >= 2 and change <= a.tol:
+            Zt = Z[:, order[:k - Q.shape[1]]].astype(np.float32)
+            Vt, Wt, lt = V @ Zt, W @ Zt, lam[order[:k - Q.shape[1]]]
+            ra = np.linalg.norm(Wt - Vt * lt[None, :].astype(np.float32), axis=0)
+            fp = beta / (1.0 - beta * lt) ** 2
+            print('  %s residual ||f(A)v - f(l)v|| / sigma_max ~ %.3g  (max over the active top values)' % (mode, float(np.max(fp * ra) / sig[0])), flush=True)
             return it, sweeps, err
         Zr = Z[:, order].astype(np.float32)
         Vr = V @ Zr; Wr = W @ Zr; lamr = lam[order]; gr = g[order]
