@@ -19,9 +19,17 @@ ap.add_argument('--sbm', type=int, default=0)
 ap.add_argument('--oversample', type=int, default=16)
 ap.add_argument('--warm', type=int, default=3)
 ap.add_argument('--no-exact', action='store_true')
+ap.add_argument('--fixture', action='store_true', help='the reference SBM fixture (1024 nodes), tests/golden/sbm1024.npz')
 a = ap.parse_args()
-csr = synth.sbm(n=a.sbm, block=1000) if a.sbm else synth.rmat(scale=a.scale)
-A = csr.to_scipy().astype(np.float32)
+if a.fixture:
+    import scipy.sparse as sp
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests/golden/sbm1024.npz'))
+    nodes = z['nodes']; pos = {int(u): i for i, u in enumerate(nodes)}
+    A = sp.csr_matrix((np.ones(len(z['src']), np.float32), ([pos[int(u)] for u in z['src']], [pos[int(v)] for v in z['dst']])), shape=(len(nodes),) * 2)
+    a.sbm = 1
+else:
+    csr = synth.sbm(n=a.sbm, block=1000) if a.sbm else synth.rmat(scale=a.scale)
+    A = csr.to_scipy().astype(np.float32)
 n = A.shape[0]
 rho = 1.0 if a.sbm else float(sla.eigsh(A.astype(np.float64), k=1, which='LA', return_eigenvectors=False)[0])
 beta = 0.01 if a.sbm else 0.5 / rho
@@ -42,11 +50,32 @@ def gram(P, Q):
     return (P.T @ Q).astype(np.float64)
 
 
+PIVOT = float(os.environ.get('PIVOT', '0'))      # 1e-5 = the GPU kernel's rule: smaller pivots drop the column
+
+
 def cholqr_pass(F):
     G = gram(F, F)
     dsc = 1.0 / np.sqrt(np.maximum(np.diag(G), 1e-300))
-    L = np.linalg.cholesky(G * dsc[:, None] * dsc[None, :] + 1e-10 * np.eye(G.shape[0]))
-    return F @ (np.linalg.inv(L).T * dsc[:, None]).astype(np.float32)
+    Gs = G * dsc[:, None] * dsc[None, :]
+    if PIVOT <= 0:
+        L = np.linalg.cholesky(Gs + 1e-10 * np.eye(G.shape[0]))
+        return F @ (np.linalg.inv(L).T * dsc[:, None]).astype(np.float32)
+    m = Gs.shape[0]
+    L = np.zeros_like(Gs); keep = np.ones(m, dtype=bool); Gw = Gs.copy()
+    for j in range(m):                                  # right-looking Cholesky with the kernel's pivot rule
+        d = Gw[j, j]
+        if d > PIVOT:
+            L[j, j] = np.sqrt(d)
+            L[j + 1:, j] = Gw[j + 1:, j] / L[j, j]
+            Gw[j + 1:, j + 1:] -= np.outer(L[j + 1:, j], L[j + 1:, j])
+        else:
+            keep[j] = False
+            L[j, j] = 1.0
+    Li = np.linalg.inv(L)
+    Li[~keep, :] = 0.0; Li[:, ~keep] = 0.0
+    if (~keep).any():
+        print('    cholqr: dropped %d columns' % int((~keep).sum()), flush=True)
+    return F @ (Li.T * dsc[:, None]).astype(np.float32)
 
 
 def cholqr2(F):
