@@ -17,7 +17,7 @@ UNIQUE_ID_BYTES = 128
 EXPORTS = [
     'gemb_version', 'gemb_last_error', 'gemb_device_count', 'gemb_launch_count', 'gemb_ctx_create', 'gemb_ctx_destroy',
     'gemb_host_alloc', 'gemb_host_free', 'gemb_mem_trim', 'gemb_mem_cached_bytes', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
-    'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_apply', 'gemb_hope', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
+    'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_apply', 'gemb_hope', 'gemb_hope_svd_error', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
     'gemb_edge_list_scan', 'gemb_edge_list_parse', 'gemb_edge_list_write', 'gemb_emb_read', 'gemb_emb_write',
     'gemb_recon_create', 'gemb_recon_free', 'gemb_recon_dense', 'gemb_recon_pairs', 'gemb_recon_ranks', 'gemb_recon_top',
 ]
@@ -28,7 +28,8 @@ class HopeOpts(ctypes.Structure):
                 ('max_iters', ctypes.c_int32), ('min_iters', ctypes.c_int32), ('tol', ctypes.c_float),
                 ('katz_terms', ctypes.c_int32), ('katz_tol', ctypes.c_float), ('seed', ctypes.c_uint64),
                 ('compute_residual', ctypes.c_int32), ('verbose', ctypes.c_int32),
-                ('algorithm', ctypes.c_int32), ('cheb_degree', ctypes.c_int32)]
+                ('algorithm', ctypes.c_int32), ('cheb_degree', ctypes.c_int32), ('cheb_range_log2', ctypes.c_float),
+                ('stop_rule', ctypes.c_int32), ('algorithm3_basis', ctypes.c_int32)]
 
 
 class HopeStats(ctypes.Structure):
@@ -38,7 +39,8 @@ class HopeStats(ctypes.Structure):
                 ('spmm_ms', ctypes.c_double), ('spmm_bytes', ctypes.c_double), ('dense_ms', ctypes.c_double),
                 ('comm_ms', ctypes.c_double), ('total_ms', ctypes.c_double), ('h2d_ms', ctypes.c_double),
                 ('d2h_ms', ctypes.c_double), ('norm2_A', ctypes.c_float), ('ritz_change', ctypes.c_float),
-                ('resid_max', ctypes.c_float)]
+                ('resid_max', ctypes.c_float), ('resid_est', ctypes.c_float), ('mg_mode', ctypes.c_int32),
+                ('halo_rows', ctypes.c_int64), ('push_rows', ctypes.c_int64), ('pushes', ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'struct_size'}
@@ -84,6 +86,7 @@ def lib():
     L.gemb_gram.argtypes = [vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
     L.gemb_apply.argtypes = [vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp]
     L.gemb_hope.argtypes = [vp, ctypes.c_int, f32, ctypes.POINTER(HopeOpts), vp, vp, ctypes.POINTER(HopeStats)]
+    L.gemb_hope_svd_error.argtypes = [vp, ctypes.c_int, f32, vp, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(f64)]
     L.gemb_n2v_alias.argtypes = [vp, vp, vp, vp]
     L.gemb_n2v_walks.argtypes = [vp, vp, vp, i64, ctypes.c_int, ctypes.c_int, f64, f64, i32, i64, i64, vp,
                                  ctypes.POINTER(N2VStats)]
@@ -210,6 +213,11 @@ class DeviceGraph:
     def __init__(self, ctx, n, indptr, indices, data=None, indptr_t=None, indices_t=None, data_t=None,
                  row0=0):
         self.ctx = ctx
+        if len(indptr) and int(indptr[-1]) >= 2 ** 31:
+            raise ValueError('a CSR shard holds %d nonzeros; gemb_graph_upload takes int32 offsets (< 2^31 per shard): '
+                             'shard the rows over more GPUs' % int(indptr[-1]))
+        if indptr_t is not None and len(indptr_t) and int(indptr_t[-1]) >= 2 ** 31:
+            raise ValueError('the transposed shard holds >= 2^31 nonzeros')
         indptr = np.ascontiguousarray(indptr, dtype=np.int32)
         indices = np.ascontiguousarray(indices, dtype=np.int32)
         data = None if data is None else np.ascontiguousarray(data, dtype=np.float32)
@@ -241,7 +249,9 @@ class DeviceGraph:
                      tol=float(opts.get('tol', 0.0)), katz_terms=int(opts.get('katz_terms', 0)),
                      katz_tol=float(opts.get('katz_tol', 0.0)), seed=int(opts.get('seed', 0)),
                      compute_residual=int(opts.get('compute_residual', 0)), verbose=int(opts.get('verbose', 0)),
-                     algorithm=int(opts.get('algorithm', 0)), cheb_degree=int(opts.get('cheb_degree', 0)))
+                     algorithm=int(opts.get('algorithm', 0)), cheb_degree=int(opts.get('cheb_degree', 0)),
+                     cheb_range_log2=float(opts.get('cheb_range_log2', 0.0)), stop_rule=int(opts.get('stop_rule', 0)),
+                     algorithm3_basis=int(opts.get('algorithm3_basis', 0)))
         st = HopeStats(struct_size=ctypes.sizeof(HopeStats))
         X = sig = None
         if want_output:
@@ -250,6 +260,14 @@ class DeviceGraph:
             sig = np.empty(d // 2, dtype=np.float32)
         check(lib().gemb_hope(self._h, int(d), float(beta), ctypes.byref(o), _ptr(X), _ptr(sig), ctypes.byref(st)))
         return X, sig, st.as_dict()
+
+    def hope_svd_error(self, d, beta, X, n_probe=0, seed=1):
+        """|| X1 X2^T - S ||_F (hope.py:38-40): exact (n_probe = 0) or a Hutchinson estimate."""
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        assert X.shape == (self.n, d)
+        err = ctypes.c_double(0.0)
+        check(lib().gemb_hope_svd_error(self._h, int(d), float(beta), _ptr(X), int(n_probe), int(seed), ctypes.byref(err)))
+        return float(err.value)
 
     def n2v_alias(self, weights64=None):
         w = None if weights64 is None else np.ascontiguousarray(weights64, dtype=np.float64)

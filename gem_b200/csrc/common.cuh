@@ -91,6 +91,36 @@ struct gemb_csr_dev {
 };
 constexpr int SPMM_HEAVY_DEG = 128, SPMM_HEAVY_CHUNK = 512;
 
+// Multi-GPU HOPE on a symmetric shard: "needed rows only" exchange over NVLink peer memory (halo.cu).
+// Every rank keeps its n x b work blocks as [n_shard local rows | halo_rows copies of the remote rows its CSR shard
+// references]; the kernel that PRODUCES a block (SpMM epilogue, axpby, or a stand-alone push) stores each local row
+// straight into the halo slots of the peers that reference it (P2P stores through CUDA-IPC mappings), so the next
+// sweep gathers from local HBM only.  A flag barrier over the same mappings separates the sweeps.
+constexpr int GEMB_MAX_RANKS = 8;
+constexpr int GEMB_HALO_BUFS = 8;
+struct gemb_halo {
+    bool ready = false;
+    int64_t halo_rows = 0;            // distinct remote rows this shard references
+    int64_t push_total = 0;           // (local row, peer) pairs this rank pushes per exchanged block
+    int32_t *indices_ext = nullptr;   // nnz: local column -> [0, n_shard), remote column -> n_shard + halo slot
+    int32_t *push_ptr = nullptr;      // n_local + 1
+    uint32_t *push_dst = nullptr;     // push_total: (peer << 29) | halo slot on that peer
+    // peer-mapped work buffers, each (n_shard + halo_rows) x width floats
+    int nbuf = 0, width = 0;
+    float *buf[GEMB_HALO_BUFS] = {};
+    float *peer_buf[GEMB_HALO_BUFS][GEMB_MAX_RANKS] = {};
+    unsigned long long *flags = nullptr;                      // [nranks]; peer q writes flags[q]
+    unsigned long long *peer_flags[GEMB_MAX_RANKS] = {};
+    unsigned long long epoch = 0;
+    int *timeout_flag = nullptr;                              // device: set when a barrier wait gave up
+};
+struct HaloPushArgs {                 // by-value kernel argument: where the rows of an output block also go
+    const int32_t *push_ptr;
+    const uint32_t *push_dst;
+    float4 *peer[GEMB_MAX_RANKS];     // the SAME block on every rank (own rank unused)
+    int64_t halo_row0;                // = n_shard: first halo row of a block
+};
+
 struct gemb_graph {
     gemb_ctx *ctx = nullptr;
     int64_t n = 0;        // global number of nodes
@@ -101,6 +131,7 @@ struct gemb_graph {
     bool symmetric = false;
     bool replicated = false;  // multi-GPU: the whole graph on every rank (node2vec) instead of a row shard
     gemb_csr_dev A, AT;   // AT aliases A when symmetric
+    gemb_halo halo;       // multi-GPU symmetric shards (built on first use)
 };
 
 namespace gemb {
@@ -112,7 +143,18 @@ int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, flo
                 const float *X, const float *X0, float *Y);
 // Y = alpha * A * X + gamma * Xself + delta * X0   (Xself / X0: row shards, may be null)
 int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha, const float *X,
-                 float gamma, const float *Xself, float delta, const float *X0, float *Y);
+                 float gamma, const float *Xself, float delta, const float *X0, float *Y,
+                 const HaloPushArgs *push = nullptr);
+
+// ---- halo.cu (multi-GPU)
+int halo_build(gemb_graph *g);                                   // collective; idempotent
+int halo_buffers(gemb_graph *g, int nbuf, int width);            // collective; (re)allocates + IPC-maps the work blocks
+int halo_push_launch(gemb_graph *g, int buf_index, int width);   // stand-alone push of a block's local rows
+int halo_barrier(gemb_graph *g);                                 // all ranks' pushes issued before it have landed
+void halo_push_args(const gemb_graph *g, int buf_index, HaloPushArgs *out);
+int halo_free(gemb_graph *g);
+// Y = a P + c Q over the local rows of halo blocks, pushing Y's rows to the peers (Chebyshev first step)
+int halo_check_timeout(gemb_graph *g);
 
 // ---- dense.cu
 // G[b1 x b2] (fp64, row-major, OVERWRITTEN) = P^T Q over n rows (P: n x b1, Q: n x b2, fp32).

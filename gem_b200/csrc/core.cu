@@ -74,7 +74,7 @@ NcclApi *nccl_api() {
         g_nccl_state = -1;                                              \
         return nullptr;                                                 \
     }
-    LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(AllGather)
+    LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllReduce) LOAD(AllGather) LOAD(Broadcast)
     LOAD(GetErrorString) LOAD(GetVersion)
 #undef LOAD
     g_nccl_state = 1;
@@ -278,7 +278,22 @@ int gemb_comm_init(gemb_ctx *c, int rank, int nranks, const void *idp) {
     return GEMB_OK;
 }
 
-static int upload_csr(gemb_ctx *c, int64_t n_local, const int32_t *indptr, const int32_t *indices,
+// flags[0] |= 1: offsets not monotone; |= 2: a column id outside [0, n)   (a malformed CSR must fail
+// loudly at upload, not read out of bounds in the sweeps)
+__global__ void csr_validate_kernel(int64_t n_local, int64_t nnz, int64_t n, const int32_t *__restrict__ indptr,
+                                    const int32_t *__restrict__ indices, int *__restrict__ flags) {
+    int bad = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_local; r += stride)
+        if (indptr[r + 1] < indptr[r]) bad |= 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const int32_t cidx = indices[i];
+        if (cidx < 0 || (int64_t)cidx >= n) bad |= 2;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
+static int upload_csr(gemb_ctx *c, int64_t n, int64_t n_local, const int32_t *indptr, const int32_t *indices,
                       const float *data, gemb_csr_dev *d) {
     int64_t nnz = indptr[n_local] - indptr[0];
     GEMB_ARG(indptr[0] == 0, "indptr[0] must be 0 (shard-local offsets)");
@@ -295,6 +310,21 @@ static int upload_csr(gemb_ctx *c, int64_t n_local, const int32_t *indptr, const
         GEMB_CUDA(dmalloc(&d->data, sizeof(float) * nnz));
         GEMB_CUDA(cudaMemcpyAsync(d->data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice,
                                   c->stream));
+    }
+    {
+        int *flags = nullptr, h = 0;
+        GEMB_CUDA(dmalloc(&flags, sizeof(int)));
+        GEMB_CUDA(cudaMemsetAsync(flags, 0, sizeof(int), c->stream));
+        csr_validate_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(n_local, nnz, n, d->indptr, d->indices, flags);
+        count_launch();
+        GEMB_CUDA(cudaMemcpyAsync(&h, flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        dfree(flags);
+        if (h) {
+            set_error("malformed CSR:%s%s", (h & 1) ? " row offsets are not monotone;" : "",
+                      (h & 2) ? " a column id lies outside [0, n)" : "");
+            return GEMB_ERR_ARG;
+        }
     }
     // heavy rows -> chunk work items (see common.cuh); one pass over the host offsets
     std::vector<int32_t> hrow, hfirst, irow, ibeg;
@@ -353,10 +383,10 @@ int gemb_graph_upload(gemb_ctx *c, int64_t n, int64_t row0, int64_t n_local, con
             return GEMB_ERR_ARG;
         }
     }
-    int s = upload_csr(c, n_local, indptr, indices, data, &g->A);
+    int s = upload_csr(c, n, n_local, indptr, indices, data, &g->A);
     if (s != GEMB_OK) { gemb_graph_free(g); return s; }
     if (indptr_t) {
-        s = upload_csr(c, n_local, indptr_t, indices_t, data_t, &g->AT);
+        s = upload_csr(c, n, n_local, indptr_t, indices_t, data_t, &g->AT);
         if (s != GEMB_OK) { gemb_graph_free(g); return s; }
         g->symmetric = false;
     } else {
@@ -375,6 +405,7 @@ int gemb_graph_upload(gemb_ctx *c, int64_t n, int64_t row0, int64_t n_local, con
 int gemb_graph_free(gemb_graph *g) {
     if (!g) return GEMB_OK;
     cudaSetDevice(g->ctx->device);
+    gemb::halo_free(g);   // collective when a halo exchange was set up (every rank frees its shard)
     if (!g->symmetric) {
         dfree(g->AT.indptr);
         dfree(g->AT.indices);

@@ -52,8 +52,11 @@ struct HopeWork {
     float *Minv = nullptr, *M1 = nullptr, *M2 = nullptr;
     int *rank_dev = nullptr;
     int64_t spmm_wide = 0, spmm_all = 0;
+    bool halo = false;       // multi-GPU: needed-rows-only exchange over peer memory (halo.cu); buf[] = g->halo.buf[]
+    int64_t pushes = 0;      // blocks whose rows were pushed to the peers
+    int buf_index(const float *p) const { for (int i = 0; i < 5; i++) if (buf[i] == p) return i; return -1; }
     ~HopeWork() {
-        for (auto p : buf) dfree(p);
+        if (!halo) for (auto p : buf) dfree(p);
         dfree(full); dfree(G); dfree(G2); dfree(w); dfree(Z); dfree(Zs); dfree(scal);
         dfree(Minv); dfree(M1); dfree(M2); dfree(rank_dev);
     }
@@ -62,7 +65,7 @@ struct HopeWork {
 struct HopeResult {
     int iters = 0, converged = 0, katz_terms = 0, algorithm = 0;
     double change = 0.0;
-    float resid_max = -1.f;
+    float resid_max = -1.f, resid_est = -1.f;
     float *Xd = nullptr;       // device n_local x d (points into a work buffer or Xalloc)
     float *Xalloc = nullptr;   // owned
     float *sig_dev = nullptr;  // k floats
@@ -91,9 +94,43 @@ static int comm_allreduce_f64(HopeWork &W, double *buf, size_t count) {
     return GEMB_OK;
 }
 
-// Y(shard) = alpha * op(A) * X + gamma * X(shard) + delta * X0(shard); X is all-gathered first when sharded
+// halo mode: the local rows of block `buf` go to the peers that reference them, then the sweep barrier
+static int publish(HopeWork &W, const float *buf, int width) {
+    if (!W.halo) return GEMB_OK;
+    const int bi = W.buf_index(buf);
+    GEMB_ARG(bi >= 0, "publish: not a work block");
+    GEMB_TRY(W.c->t_comm.begin(W.c->stream));
+    GEMB_TRY(halo_push_launch(W.g, bi, width));
+    GEMB_TRY(halo_barrier(W.g));
+    GEMB_TRY(W.c->t_comm.end(W.c->stream));
+    W.pushes++;
+    return GEMB_OK;
+}
+
+// Y(shard) = alpha * op(A) * X + gamma * X(shard) + delta * X0(shard).  Sharded: halo mode gathers from the block's own
+// [local | halo] rows and (push_out) stores Y's rows into the peers' halo slots from the epilogue; otherwise X is
+// all-gathered first.
 static int dist_spmm3(HopeWork &W, bool transpose, int width, float alpha, const float *Xshard, float gamma,
-                      bool use_self, float delta, const float *X0, float *Y, bool timed) {
+                      bool use_self, float delta, const float *X0, float *Y, bool timed, bool push_out = false) {
+    if (W.halo) {
+        gemb_csr_dev A = W.g->A;
+        A.indices = W.g->halo.indices_ext;
+        HaloPushArgs P;
+        const int bo = W.buf_index(Y);
+        if (push_out) { GEMB_ARG(bo >= 0, "spmm output is not a work block"); halo_push_args(W.g, bo, &P); }
+        if (timed) GEMB_TRY(W.c->t_spmm.begin(W.c->stream));
+        GEMB_TRY(spmm3_launch(W.c, A, W.rows, width, alpha, Xshard, gamma, use_self ? Xshard : nullptr, delta, X0, Y,
+                              push_out ? &P : nullptr));
+        if (timed) { GEMB_TRY(W.c->t_spmm.end(W.c->stream)); W.spmm_wide++; }
+        W.spmm_all++;
+        if (push_out) {
+            GEMB_TRY(W.c->t_comm.begin(W.c->stream));
+            GEMB_TRY(halo_barrier(W.g));
+            GEMB_TRY(W.c->t_comm.end(W.c->stream));
+            W.pushes++;
+        }
+        return GEMB_OK;
+    }
     const float *Xfull = Xshard;
     if (W.c->nranks > 1) {
         GEMB_TRY(comm_allgather(W, Xshard, width));
@@ -118,8 +155,8 @@ static int katz(HopeWork &W, bool transpose, float beta, int J, const float *in,
     const float *cur = in;
     for (int m = 1; m <= J; m++) {
         if (m < J) {
-            float *dst = (m & 1) ? t1 : t2;
-            GEMB_TRY(dist_spmm(W, transpose, W.b, beta, cur, in, dst, true));
+            float *dst = (m & 1) ? t1 : t2;   // halo mode: `in` was published by the caller, dst feeds the next sweep
+            GEMB_TRY(dist_spmm3(W, transpose, W.b, beta, cur, 0.f, false, 1.f, in, dst, true, W.halo));
             cur = dst;
         } else {
             GEMB_TRY(dist_spmm(W, transpose, W.b, beta, cur, nullptr, out, true));
@@ -209,8 +246,42 @@ __global__ void axpby_kernel(int64_t count, float a, const float4 *__restrict__ 
     }
 }
 
+// the same, one thread group per row, storing the row into the peers' halo slots as well (halo mode)
+__global__ void __launch_bounds__(256)
+axpby_push_kernel(int64_t n_rows, int G, int rows_per_cta, float a, const float4 *__restrict__ P, float c,
+                  const float4 *__restrict__ Q, float4 *__restrict__ Y, HaloPushArgs H) {
+    const int lr = threadIdx.x / G, cc = threadIdx.x - lr * G;
+    if (lr >= rows_per_cta) return;
+    const int64_t row = (int64_t)blockIdx.x * rows_per_cta + lr;
+    if (row >= n_rows) return;
+    const float4 p = P[row * G + cc], q = Q[row * G + cc];
+    const float4 v = make_float4(a * p.x + c * q.x, a * p.y + c * q.y, a * p.z + c * q.z, a * p.w + c * q.w);
+    Y[row * G + cc] = v;
+    for (int i = H.push_ptr[row], e = H.push_ptr[row + 1]; i < e; i++) {
+        const uint32_t d = H.push_dst[i];
+        H.peer[d >> 29][(H.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + cc] = v;
+    }
+}
+
 static int axpby_launch(HopeWork &W, float a, const float *P, float c, const float *Q, float *Y) {
     const int64_t count = W.rows * (int64_t)W.b / 4;
+    if (W.halo) {        // Y feeds the next SpMM: its rows go to the peers from here
+        const int G = W.b / 4, rpc = 256 / G, bo = W.buf_index(Y);
+        GEMB_ARG(bo >= 0 && G <= 256, "axpby output is not a work block");
+        HaloPushArgs H;
+        halo_push_args(W.g, bo, &H);
+        if (W.rows > 0) {
+            axpby_push_kernel<<<(unsigned)((W.rows + rpc - 1) / rpc), 256, 0, W.c->stream>>>(
+                W.rows, G, rpc, a, (const float4 *)P, c, (const float4 *)Q, (float4 *)Y, H);
+            GEMB_CUDA(cudaGetLastError());
+            count_launch();
+        }
+        GEMB_TRY(W.c->t_comm.begin(W.c->stream));
+        GEMB_TRY(halo_barrier(W.g));
+        GEMB_TRY(W.c->t_comm.end(W.c->stream));
+        W.pushes++;
+        return GEMB_OK;
+    }
     if (count == 0) return GEMB_OK;
     int grid = W.c->sm_count * 8;
     if ((int64_t)grid * 256 > count) grid = (int)((count + 255) / 256);
@@ -279,7 +350,8 @@ static int estimate_norm2(HopeWork &W, uint64_t seed, float *x, float *y, float 
     for (int it = 0; it < 16; it++) {
         double h[2];
         GEMB_TRY(sumsq_launch(c, W.rows * pw, x, W.scal));
-        GEMB_TRY(dist_spmm(W, false, pw, 1.f, x, nullptr, y, false));
+        GEMB_TRY(publish(W, x, pw));
+        GEMB_TRY(dist_spmm3(W, false, pw, 1.f, x, 0.f, false, 1.f, nullptr, y, false, true));
         GEMB_TRY(dist_spmm(W, true, pw, 1.f, y, nullptr, z, false));
         GEMB_TRY(sumsq_launch(c, W.rows * pw, z, W.scal + 1));
         GEMB_TRY(comm_allreduce_f64(W, W.scal, 2));
@@ -296,10 +368,47 @@ static int estimate_norm2(HopeWork &W, uint64_t seed, float *x, float *y, float 
     return GEMB_OK;
 }
 
+// beta * ||A||_2 >= 1 does not mean the Katz series diverges: it converges iff beta * rho(A) < 1, and a directed graph
+// (a hub, a DAG: rho = 0) can have ||A||_2 far above rho(A).  Measure the series itself on a width-4 random probe:
+// t_j = (beta op(A))^j t_0; J = first j with ||t_j|| <= katz_tol * max_i ||t_i|| (for A and A^T), plus a margin.
+// Returns GEMB_ERR_DIVERGE when the terms do not decay (rho_est = last growth ratio / beta).
+static int probe_katz_terms(HopeWork &W, float beta, double katz_tol, uint64_t seed, float *x, float *y, int *J_out,
+                            double *rho_est) {
+    gemb_ctx *c = W.c;
+    const int pw = 4, Jmax = 2048;
+    int Jbest = 1;
+    *rho_est = 0.0;
+    for (int tr = 0; tr < 2; tr++) {
+        GEMB_TRY(randn_launch(c, W.rows, pw, seed ^ (0x7f4a7c15u + tr), (uint64_t)W.g->row0, x));
+        double peak = 0.0, prev = 0.0;
+        int j = 0;
+        bool done = false;
+        for (j = 1; j <= Jmax; j++) {
+            double h = 0.0;
+            GEMB_TRY(dist_spmm(W, tr == 1, pw, beta, x, nullptr, y, false));
+            GEMB_TRY(sumsq_launch(c, W.rows * pw, y, W.scal));
+            GEMB_TRY(comm_allreduce_f64(W, W.scal, 1));
+            GEMB_CUDA(cudaMemcpyAsync(&h, W.scal, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+            GEMB_CUDA(cudaStreamSynchronize(c->stream));
+            const double nt = sqrt(h);
+            if (prev > 0.0) *rho_est = std::max(*rho_est * (j > 8 ? 0.0 : 1.0), nt / prev / (double)beta);
+            if (!(nt < 1e30)) break;
+            peak = std::max(peak, nt);
+            if (nt <= katz_tol * peak) { done = true; break; }
+            prev = nt;
+            std::swap(x, y);
+        }
+        if (!done) return GEMB_ERR_DIVERGE;
+        Jbest = std::max(Jbest, j);
+    }
+    *J_out = std::min(4096, Jbest + Jbest / 8 + 2);
+    return GEMB_OK;
+}
+
 struct Opts {
     int oversample = 16, max_iters = 30, min_iters = 2, katz_terms = 0, compute_residual = 0, verbose = 0;
-    int algorithm = 0, cheb_degree = 8;
-    float tol = 1e-6f, katz_tol = 1e-7f;
+    int algorithm = 0, cheb_degree = 8, stop_rule = 0, lanczos_basis = 0;
+    float tol = 1e-6f, katz_tol = 1e-7f, range_log2 = 8.f;
     uint64_t seed = 1234;
 };
 
@@ -459,12 +568,15 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
 
     GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)W.g->row0, pool[0]));
     GEMB_TRY(cholqr2(W, pool[0], pool[1], V));
+    GEMB_TRY(publish(W, V, b));
     for (int s = 0; s < 3; s++) {   // warm-up: plain power steps V <- orth(A V) (no Rayleigh-Ritz needed yet)
         GEMB_TRY(dist_spmm(W, false, b, 1.f, V, nullptr, AV, true));
         GEMB_TRY(cholqr2(W, AV, pool[0], V));
+        GEMB_TRY(publish(W, V, b));
     }
 
     std::vector<double> lam(b), gval(b), th_sorted(b), th_prev(b, 0.0);
+    std::vector<double> Wh(o.stop_rule == 1 ? (size_t)b * b : 0), Zr(o.stop_rule == 1 ? (size_t)b * b : 0);
     std::vector<int> order(b);
     struct Plan { bool valid = false; int deg = 0; double e = 0, c0 = 0, sigma1 = 0; } plan;
 
@@ -481,7 +593,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
             const double sn = 1.0 / (tau2 - sigma);
             float *nxt = free_a;
             GEMB_TRY(dist_spmm3(W, false, b, (float)(2.0 * sn / e), cur, (float)(-2.0 * sn * c0 / e), true,
-                                (float)(-sigma * sn), prev, nxt, true));
+                                (float)(-sigma * sn), prev, nxt, true, /*push_out=*/i < pl.deg));
             sigma = sn;
             // rotate: the old `prev` becomes free unless it is V (V must survive until the new basis exists)
             float *old_prev = prev;
@@ -531,10 +643,36 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         }
         R.change = change;
         th_prev = th_sorted;
+        double stop_measure = change;
+        if (o.stop_rule == 1) {
+            // residual of the Ritz pairs from the Rayleigh-Ritz products alone: with V orthonormal and (l, z) an
+            // eigenpair of V^T A V,  ||A V z - l V z||^2 = z^T (AV)^T (AV) z - l^2.  Mapped to the Katz operator
+            // through |f'(l)| = beta / (1 - beta l)^2 and measured against sigma_max, like compute_residual does.
+            GEMB_TRY(gram_full(W, AV, AV, W.G));
+            GEMB_CUDA(cudaMemcpyAsync(Wh.data(), W.G, sizeof(double) * b * b, cudaMemcpyDeviceToHost, c->stream));
+            GEMB_CUDA(cudaMemcpyAsync(Zr.data(), W.Z, sizeof(double) * b * b, cudaMemcpyDeviceToHost, c->stream));
+            GEMB_CUDA(cudaStreamSynchronize(c->stream));
+            double worst = 0.0;
+            for (int j = 0; j < k; j++) {
+                const int col = order[j];
+                double q = 0.0;
+                for (int r = 0; r < b; r++) {
+                    double t = 0.0;
+                    for (int s2 = 0; s2 < b; s2++) t += Wh[(size_t)r * b + s2] * Zr[(size_t)s2 * b + col];
+                    q += Zr[(size_t)r * b + col] * t;
+                }
+                const double l = std::max(-bound, std::min(bound, lam[col]));
+                const double r2 = std::max(q - lam[col] * lam[col], 0.0);
+                const double fp = (double)beta / ((1.0 - beta * l) * (1.0 - beta * l));
+                worst = std::max(worst, fp * sqrt(r2) / std::max(gval[order[0]], 1e-300));
+            }
+            stop_measure = worst;
+            R.resid_est = (float)worst;
+        }
         if (o.verbose)
-            fprintf(stderr, "[gemb_hope/symmetric] it %d  sigma_max %.6g sigma_k %.6g  ritz change %.3g\n", it,
-                    gval[order[0]], gval[order[k - 1]], change);
-        if (it >= o.min_iters && change <= (double)o.tol) { R.converged = 1; break; }
+            fprintf(stderr, "[gemb_hope/symmetric] it %d  sigma_max %.6g sigma_k %.6g  ritz change %.3g%s%.3g\n", it,
+                    gval[order[0]], gval[order[k - 1]], change, o.stop_rule == 1 ? "  residual " : " ", o.stop_rule == 1 ? stop_measure : 0.0);
+        if (it >= o.min_iters && stop_measure <= (double)o.tol) { R.converged = 1; break; }
         if (it == o.max_iters) break;
 
         // damped set {l : |f(l)| < tau}, tau = smallest |f| in the block
@@ -559,12 +697,13 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         // (scripts/proto_bcgs.py) says that the column scaling inside the Ritz-rotated CholeskyQR tolerates far
         // more than 2^8 on the SBM spectrum (degree 12: residual 3.8e-3 after 4 rounds / 40 sweeps instead of 4.9e-3
         // after 8 rounds / 56 sweeps), which is to be confirmed on the GPU before the default moves.
-        static const double range_log2 = getenv("GEMB_CHEB_RANGE_LOG2") ? atof(getenv("GEMB_CHEB_RANGE_LOG2")) : 8.0;
+        const double range_log2 = getenv("GEMB_CHEB_RANGE_LOG2") ? atof(getenv("GEMB_CHEB_RANGE_LOG2")) : (double)o.range_log2;
         if (growth > 1.0 + 1e-9) np.deg = std::min(np.deg, (int)floor(log(2.0 * exp2(range_log2)) / log(growth)));
 
         if (!filtered) {
             if (np.deg < 2) {                                          // A V is already there: one power step
                 GEMB_TRY(orth_rotated(W, AV, pool[0], V));
+                GEMB_TRY(publish(W, V, b));
                 plan = np;
                 continue;
             }
@@ -576,6 +715,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         for (float *cand : {pool[0], pool[1], pool[2], AV})
             if (cand != filtered) { tmp = cand; break; }
         GEMB_TRY(orth_rotated(W, filtered, tmp, V));
+        GEMB_TRY(publish(W, V, b));
     }
 
     // ---- extraction: top k by |f|, ascending sigma
@@ -625,31 +765,126 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
                 MQ[(size_t)i * b + col] = (float)(z * fabs(f));       // v sigma
             }
         }
-        float *dMP = nullptr, *dMQ = nullptr, *P = nullptr, *Q = nullptr, *STP = nullptr;
+        float *dMP = nullptr, *dMQ = nullptr, *Palloc = nullptr, *Q = nullptr, *STP = nullptr;
         const size_t blk = sizeof(float) * (size_t)W.shard * b;
         GEMB_CUDA(dmalloc(&dMP, sizeof(float) * b * b));
         GEMB_CUDA(dmalloc(&dMQ, sizeof(float) * b * b));
-        GEMB_CUDA(dmalloc(&P, blk ? blk : 4));
+        // every SpMM INPUT must be a work block in halo mode (its rows travel to the peers): P lives in AV, the Horner
+        // scratch in pool[1] / pool[2]; pool[0] may hold the result X and stays untouched
+        float *P = AV;
+        if (!W.halo) { GEMB_CUDA(dmalloc(&Palloc, blk ? blk : 4)); GEMB_CUDA(cudaMemsetAsync(Palloc, 0, blk, c->stream)); P = Palloc; }
         GEMB_CUDA(dmalloc(&Q, blk ? blk : 4));
         GEMB_CUDA(dmalloc(&STP, blk ? blk : 4));
-        GEMB_CUDA(cudaMemsetAsync(P, 0, blk, c->stream));
         GEMB_CUDA(cudaMemsetAsync(Q, 0, blk, c->stream));
         GEMB_CUDA(cudaMemsetAsync(STP, 0, blk, c->stream));
         GEMB_CUDA(cudaMemcpyAsync(dMP, MP.data(), sizeof(float) * b * b, cudaMemcpyHostToDevice, c->stream));
         GEMB_CUDA(cudaMemcpyAsync(dMQ, MQ.data(), sizeof(float) * b * b, cudaMemcpyHostToDevice, c->stream));
         int s = apply_launch(c, W.rows, V, b, dMP, b, b, P, b);
         if (s == GEMB_OK) s = apply_launch(c, W.rows, V, b, dMQ, b, b, Q, b);
-        if (s == GEMB_OK) s = residual_check(W, beta, J, P, Q, STP, AV, pool[1], sel, R.sigma_max, &R.resid_max);
+        if (s == GEMB_OK) s = publish(W, P, b);
+        if (s == GEMB_OK) s = residual_check(W, beta, J, P, Q, STP, W.halo ? pool[1] : AV, W.halo ? pool[2] : pool[1], sel, R.sigma_max, &R.resid_max);
         cudaStreamSynchronize(c->stream);
-        dfree(dMP); dfree(dMQ); dfree(P); dfree(Q); dfree(STP);
+        dfree(dMP); dfree(dMQ); dfree(Palloc); dfree(Q); dfree(STP);
         if (s != GEMB_OK) return s;
     }
     return GEMB_OK;
 }
 
+// ---- 'SVD error (low rank)' of hope.py:38-40
+__global__ void split_halves_kernel(int64_t n, int d, const float *__restrict__ X, float *__restrict__ L, float *__restrict__ Rr) {
+    const int k = d / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * d; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / d;
+        const int cc = (int)(i - r * d);
+        if (cc < k) L[r * k + cc] = X[i]; else Rr[r * k + (cc - k)] = X[i];
+    }
+}
+// Z (n x w): identity columns p0 .. p0+w-1 (exact mode) or Rademacher +-1 (probe mode)
+__global__ void probe_block_kernel(int64_t n, int w, int64_t p0, int probe, uint64_t seed, float *__restrict__ Z) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * w; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / w;
+        const int cc = (int)(i - r * w);
+        float v;
+        if (probe) {
+            uint64_t h = seed ^ ((uint64_t)r * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(p0 + cc) * 0xBF58476D1CE4E5B9ull);
+            h ^= h >> 31; h *= 0x94D049BB133111EBull; h ^= h >> 29;
+            v = (h & 1) ? 1.f : -1.f;
+        } else v = (r == p0 + cc) ? 1.f : 0.f;
+        Z[i] = v;
+    }
+}
+__global__ void f64_to_f32_kernel(int count, const double *__restrict__ a, float *__restrict__ o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) o[i] = (float)a[i];
+}
+
 }  // namespace gemb
 
 using namespace gemb;
+
+extern "C" int gemb_hope_svd_error(gemb_graph *g, int d, float beta, const float *X, int n_probe, uint64_t seed,
+                                   double *err_out) {
+    GEMB_ARG(g && X && err_out, "graph/X/err_out");
+    GEMB_ARG(d >= 2 && d % 2 == 0, "d must be even");
+    gemb_ctx *c = g->ctx;
+    GEMB_ARG(c->nranks == 1 && g->n_local == g->n, "gemb_hope_svd_error is single-GPU");
+    GEMB_CUDA(cudaSetDevice(c->device));
+    const int64_t n = g->n;
+    const int k = d / 2;
+    const bool probe = n_probe > 0;
+    const int w = (int)std::min<int64_t>(64, probe ? ((n_probe + 3) / 4 * 4) : ((n + 3) / 4 * 4));   // panel width
+    HopeWork W;
+    W.g = g; W.c = c; W.b = w; W.rows = n; W.shard = n;
+    const size_t blk = sizeof(float) * (size_t)n * w;
+    for (int i = 0; i < 5; i++) { GEMB_CUDA(dmalloc(&W.buf[i], blk)); GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream)); }
+    GEMB_CUDA(dmalloc(&W.scal, sizeof(double) * (w + 8)));
+    GEMB_CUDA(dmalloc(&W.G, sizeof(double) * (size_t)k * w));
+    GEMB_CUDA(dmalloc(&W.M1, sizeof(float) * (size_t)k * w));
+    float *Xd = nullptr, *L = nullptr, *Rr = nullptr;
+    GEMB_CUDA(dmalloc(&Xd, sizeof(float) * (size_t)n * d));
+    GEMB_CUDA(dmalloc(&L, sizeof(float) * (size_t)n * k));
+    GEMB_CUDA(dmalloc(&Rr, sizeof(float) * (size_t)n * k));
+    struct Guard { float *a, *b, *c; ~Guard() { dfree(a); dfree(b); dfree(c); } } guard{Xd, L, Rr};
+    GEMB_CUDA(cudaMemcpyAsync(Xd, X, sizeof(float) * (size_t)n * d, cudaMemcpyHostToDevice, c->stream));
+    split_halves_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(n, d, Xd, L, Rr);
+    GEMB_CUDA(cudaGetLastError());
+    count_launch();
+    c->t_spmm.reset(); c->t_dense.reset(); c->t_comm.reset();
+    double nrm = 0.0;
+    GEMB_TRY(estimate_norm2(W, seed ? seed : 1, W.buf[3], W.buf[4], W.buf[2], &nrm));
+    if ((double)beta * nrm * 1.02 >= 1.0) {
+        set_error("beta * ||A||_2 = %.4g >= 1: the Katz series does not converge", (double)beta * nrm);
+        return GEMB_ERR_DIVERGE;
+    }
+    const int J = katz_terms_for(beta, nrm, 1e-9);
+    for (int i = 2; i < 5; i++) GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));
+    float *Z = W.buf[0], *SZ = W.buf[1], *LZ = W.buf[2];
+    const int64_t total_cols = probe ? n_probe : n;
+    double acc = 0.0;
+    std::vector<double> rs(w);
+    const int threads = (256 / w) * w > 0 ? (256 / w) * w : w;
+    for (int64_t p0 = 0; p0 < total_cols; p0 += w) {
+        const int live = (int)std::min<int64_t>(w, total_cols - p0);
+        probe_block_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(n, w, p0, probe ? 1 : 0, seed, Z);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+        GEMB_TRY(katz(W, false, beta, J, Z, SZ, W.buf[3], W.buf[4]));             // S Z
+        GEMB_TRY(gram_launch(c, n, Rr, k, Z, w, W.G));                            // X2^T Z   (k x w, fp64)
+        f64_to_f32_kernel<<<(k * w + 255) / 256, 256, 0, c->stream>>>(k * w, W.G, W.M1);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+        GEMB_TRY(apply_launch(c, n, L, k, W.M1, w, w, LZ, w));                    // X1 (X2^T Z)
+        GEMB_CUDA(cudaMemsetAsync(W.scal, 0, sizeof(double) * w, c->stream));
+        coldiff_sumsq_kernel<<<c->sm_count * 4, threads, 0, c->stream>>>(n, w, LZ, SZ, W.scal);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+        GEMB_CUDA(cudaMemcpyAsync(rs.data(), W.scal, sizeof(double) * w, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int j = 0; j < live; j++) acc += rs[j];
+    }
+    *err_out = sqrt(probe ? acc / (double)n_probe : acc);
+    return GEMB_OK;
+}
 
 extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts *uo, float *X_out,
                          float *sigma_out, gemb_hope_stats *stats) {
@@ -671,12 +906,16 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         if (uo->seed) o.seed = uo->seed;
         o.compute_residual = uo->compute_residual;
         o.verbose = uo->verbose;
-        GEMB_ARG(uo->algorithm >= 0 && uo->algorithm <= 2, "opts.algorithm");
+        GEMB_ARG(uo->algorithm >= 0 && uo->algorithm <= 3, "opts.algorithm");
         o.algorithm = uo->algorithm;
         if (uo->cheb_degree >= 2) o.cheb_degree = uo->cheb_degree;
+        if (uo->cheb_range_log2 > 0.f) o.range_log2 = uo->cheb_range_log2;
+        GEMB_ARG(uo->stop_rule == 0 || uo->stop_rule == 1, "opts.stop_rule");
+        o.stop_rule = uo->stop_rule;
+        if (uo->algorithm3_basis > 0) o.lanczos_basis = uo->algorithm3_basis;
     }
-    if (o.algorithm == 2 && !g->symmetric) {
-        set_error("algorithm=2 (Chebyshev on A) needs a symmetric shard (upload with indptr_t = NULL)");
+    if (o.algorithm >= 2 && !g->symmetric) {
+        set_error("algorithm=%d (works on A itself, S = f(A)) needs a symmetric shard (upload with indptr_t = NULL)", o.algorithm);
         return GEMB_ERR_ARG;
     }
     const int algo = o.algorithm ? o.algorithm : (g->symmetric ? 2 : 1);
@@ -692,11 +931,35 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     HopeWork W;
     W.g = g; W.c = c; W.b = b; W.rows = g->n_local; W.shard = g->n_shard;
     const size_t blk = sizeof(float) * (size_t)W.shard * b;
-    for (int i = 0; i < 5; i++) {
-        GEMB_CUDA(dmalloc(&W.buf[i], blk ? blk : 4));
-        GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));  // padded rows stay 0
+    // multi-GPU, symmetric shard: needed-rows-only exchange over peer memory (halo.cu) unless GEMB_MG=allgather or
+    // CUDA IPC is not available on this box (then every rank falls back to the all-gather form together)
+    static const bool mg_allgather = getenv("GEMB_MG") && !strcmp(getenv("GEMB_MG"), "allgather");
+    if (c->nranks > 1 && algo >= 2 && !mg_allgather) {
+        int hs = halo_build(g);
+        if (hs == GEMB_OK) hs = halo_buffers(g, 5, b);
+        NcclApi *api = nccl_api();
+        if (!api) return GEMB_ERR_NCCL;
+        int *flag = nullptr, hflag = (hs == GEMB_OK) ? 1 : 0;
+        GEMB_CUDA(dmalloc(&flag, sizeof(int)));
+        GEMB_CUDA(cudaMemcpyAsync(flag, &hflag, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        ncclResult_t r = api->AllReduce(flag, flag, 1, ncclInt, ncclMin, (ncclComm_t)c->comm, c->stream);
+        GEMB_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        dfree(flag);
+        if (r != ncclSuccess) { set_error("ncclAllReduce(halo agreement): %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
+        W.halo = hflag == 1;
+        if (!W.halo && o.verbose) fprintf(stderr, "[gemb_hope] halo exchange unavailable (%s); all-gather per sweep\n", gemb_last_error());
     }
-    if (c->nranks > 1) GEMB_CUDA(dmalloc(&W.full, sizeof(float) * (size_t)g->n_pad * b));
+    if (W.halo) {
+        for (int i = 0; i < 5; i++) W.buf[i] = g->halo.buf[i];
+        GEMB_TRY(halo_barrier(g));    // every rank's blocks are in place before the first push can arrive
+    } else {
+        for (int i = 0; i < 5; i++) {
+            GEMB_CUDA(dmalloc(&W.buf[i], blk ? blk : 4));
+            GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));  // padded rows stay 0
+        }
+        if (c->nranks > 1) GEMB_CUDA(dmalloc(&W.full, sizeof(float) * (size_t)g->n_pad * b));
+    }
     GEMB_CUDA(dmalloc(&W.G, sizeof(double) * b * b));
     GEMB_CUDA(dmalloc(&W.G2, sizeof(double) * b * b));
     GEMB_CUDA(dmalloc(&W.Z, sizeof(double) * b * b));
@@ -727,14 +990,25 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     if (need_power) {
         GEMB_TRY(estimate_norm2(W, o.seed, W.buf[3], W.buf[4], W.buf[2], &nrm));
         if ((double)beta * nrm * 1.02 >= 1.0) {
-            set_error("beta * ||A||_2 = %.4g >= 1: the Katz series (I - beta A)^-1 beta A does not converge; "
-                      "choose beta < %.4g", (double)beta * nrm, 1.0 / nrm);
-            cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-            return GEMB_ERR_DIVERGE;
+            // symmetric A: ||A||_2 = rho(A), the series diverges.  Otherwise look at the series itself.
+            int Jp = 0;
+            double rho = nrm;
+            int ps = GEMB_ERR_DIVERGE;
+            if (algo == 1 && !W.halo) {
+                ps = probe_katz_terms(W, beta, o.katz_tol, o.seed, W.buf[3], W.buf[4], &Jp, &rho);
+                if (ps != GEMB_OK && ps != GEMB_ERR_DIVERGE) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return ps; }
+            }
+            if (ps != GEMB_OK) {
+                set_error("beta * rho(A) ~ %.4g >= 1 (||A||_2 = %.4g): the Katz series (I - beta A)^-1 beta A does not "
+                          "converge; choose beta < %.4g", (double)beta * rho, nrm, 1.0 / std::max(rho, 1e-300));
+                cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+                return GEMB_ERR_DIVERGE;
+            }
+            if (J <= 0) J = Jp;
         }
         if (J <= 0) J = katz_terms_for(beta, nrm, o.katz_tol);
         if (hard_bound <= 0.0) hard_bound = nrm;
-        for (int i = 2; i < 5; i++) GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));  // width-4 scratch
+        for (int i = 2; i < 5; i++) GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));  // width-4 scratch (local rows)
     }
 
     HopeResult R;
@@ -743,6 +1017,7 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
 
     GEMB_CUDA(cudaEventRecord(ev1, c->stream));
     GEMB_CUDA(cudaEventSynchronize(ev1));
+    if (W.halo) { const int hs = halo_check_timeout(g); if (hs != GEMB_OK) { dfree(R.Xalloc); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return hs; } }
     float total_ms = 0.f;
     GEMB_CUDA(cudaEventElapsedTime(&total_ms, ev0, ev1));
 
@@ -774,8 +1049,19 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         stats->spmm_count = W.spmm_wide;   /* block-width sweeps (norm estimation excluded) */
         stats->spmm_ms = c->t_spmm.total_ms();
         const double nnz = (double)g->A.nnz;
+        // compulsory bytes of one sweep on THIS rank: CSR + every referenced X row once + Y rows once.  Single GPU:
+        // all n rows; halo mode: the shard's own rows + the distinct remote rows it references (+ the rows it stores
+        // into the peers); all-gather mode: the shard's rows + the halo it would have needed (the gathered rest is not
+        // compulsory and is not counted -- round 1 counted the whole gathered block here).
+        double x_rows = (double)g->n;
+        if (c->nranks > 1) x_rows = (double)W.rows + (W.halo ? (double)g->halo.halo_rows : 0.0);
         stats->spmm_bytes = (g->A.data ? 8.0 : 4.0) * nnz + 4.0 * (double)(W.rows + 1) +
-                            4.0 * (double)b * ((double)g->n + (double)W.rows);
+                            4.0 * (double)b * (x_rows + (double)W.rows);
+        stats->halo_rows = W.halo ? g->halo.halo_rows : 0;
+        stats->push_rows = W.halo ? g->halo.push_total : 0;
+        stats->pushes = W.pushes;
+        stats->mg_mode = c->nranks == 1 ? 0 : (W.halo ? 2 : 1);
+        stats->resid_est = R.resid_est;
         stats->dense_ms = c->t_dense.total_ms();
         stats->comm_ms = c->t_comm.total_ms();
         stats->total_ms = total_ms;

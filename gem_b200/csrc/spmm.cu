@@ -11,6 +11,7 @@
 // gathers in flight.  The Horner epilogue (X0 + alpha * acc) is fused: one extra coalesced read.
 #include "common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace gemb {
 
@@ -24,13 +25,15 @@ __device__ __forceinline__ void fma4(float4 &a, float v, const float4 &x) {
 // Y[row] = alpha * (A X)[row] + gamma * Xself[row] + delta * X0[row]
 //   Horner / Katz sweep:      gamma = 0, delta = 1, X0 = the sweep's input block
 //   Chebyshev three-term step: gamma = -2 s c0 / e (current block), delta = -s s' (previous block)
-template <bool HAS_VAL, bool HAS_X0, bool HAS_SELF>
+// HAS_PUSH (multi-GPU, halo.cu): the finished row is also stored into the halo slots of the peers whose shards
+// reference it -- 16-byte posted stores over NVLink, issued while the other row groups of the SM are still gathering.
+template <bool HAS_VAL, bool HAS_X0, bool HAS_SELF, bool HAS_PUSH>
 __global__ void __launch_bounds__(256)
 spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                      const float *__restrict__ vals, int64_t n_rows, int G, int rows_per_cta,
                      float alpha, float gamma, float delta, const float4 *__restrict__ X,
                      const float4 *__restrict__ Xself, const float4 *__restrict__ X0,
-                     float4 *__restrict__ Y, int heavy_deg) {
+                     float4 *__restrict__ Y, int heavy_deg, HaloPushArgs P) {
     const int tid = threadIdx.x;
     const int lr = tid / G;
     const int c = tid - lr * G;
@@ -83,6 +86,12 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
         r.w = fmaf(delta, z.w, r.w);
     }
     Y[row * G + c] = r;
+    if (HAS_PUSH) {
+        for (int i2 = P.push_ptr[row], e2 = P.push_ptr[row + 1]; i2 < e2; i2++) {
+            const uint32_t d = P.push_dst[i2];
+            P.peer[d >> 29][(P.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + c] = r;
+        }
+    }
 }
 
 // ---- heavy rows (degree > SPMM_HEAVY_DEG; the hubs of a power-law graph -- R-MAT scale 21 has a 61 814-neighbour
@@ -143,7 +152,8 @@ template <bool HAS_X0, bool HAS_SELF>
 __global__ void __launch_bounds__(256)
 spmm_heavy_finish_kernel(int n_heavy, const int32_t *__restrict__ heavy_row, const int32_t *__restrict__ heavy_first,
                          int G, float alpha, float gamma, float delta, const float4 *__restrict__ partial,
-                         const float4 *__restrict__ Xself, const float4 *__restrict__ X0, float4 *__restrict__ Y) {
+                         const float4 *__restrict__ Xself, const float4 *__restrict__ X0, float4 *__restrict__ Y,
+                         bool has_push, HaloPushArgs P) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = idx / G, c = idx - h * G;
     if (h >= n_heavy) return;
@@ -164,125 +174,24 @@ spmm_heavy_finish_kernel(int n_heavy, const int32_t *__restrict__ heavy_row, con
         r.x = fmaf(delta, z.x, r.x); r.y = fmaf(delta, z.y, r.y); r.z = fmaf(delta, z.z, r.z); r.w = fmaf(delta, z.w, r.w);
     }
     Y[row * G + c] = r;
-}
-
-// ---- v2: one persistent 1024-thread CTA per SM walks whole row TILES (dynamic tile counter).  All 51 row groups
-// of an SM then gather from the same neighbourhood of X at the same time, so the rows a community shares are
-// served by that SM's L1 instead of L2 (v1 spreads consecutive row groups over all 148 SMs: 17 % L1 hits).
-template <bool HAS_VAL, bool HAS_X0, bool HAS_SELF>
-__global__ void __launch_bounds__(1024, 1)
-spmm_tile_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
-                 const float *__restrict__ vals, int64_t n_rows, int G, int groups, int tile_rows,
-                 float alpha, float gamma, float delta, const float4 *__restrict__ X,
-                 const float4 *__restrict__ Xself, const float4 *__restrict__ X0,
-                 float4 *__restrict__ Y, int *__restrict__ tile_counter) {
-    __shared__ int s_tile[2];
-    const int tid = threadIdx.x;
-    const int lr = tid / G;
-    const int c = tid - lr * G;
-    const bool active = lr < groups;
-    const float4 *Xc = X + c;
-    for (int it = 0;; it++) {
-        if (tid == 0) s_tile[it & 1] = atomicAdd(tile_counter, 1);
-        __syncthreads();
-        const int64_t r0 = (int64_t)s_tile[it & 1] * tile_rows;
-        if (r0 >= n_rows) break;
-        const int64_t r1 = r0 + tile_rows < n_rows ? r0 + tile_rows : n_rows;
-        if (active) {
-            for (int64_t row = r0 + lr; row < r1; row += groups) {
-                const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                int i = s;
-                for (; i + 4 <= e; i += 4) {
-                    const int c0 = __ldg(indices + i), c1 = __ldg(indices + i + 1);
-                    const int c2 = __ldg(indices + i + 2), c3 = __ldg(indices + i + 3);
-                    float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
-                    if (HAS_VAL) {
-                        v0 = __ldg(vals + i); v1 = __ldg(vals + i + 1);
-                        v2 = __ldg(vals + i + 2); v3 = __ldg(vals + i + 3);
-                    }
-                    const float4 x0 = __ldg(Xc + (int64_t)c0 * G);
-                    const float4 x1 = __ldg(Xc + (int64_t)c1 * G);
-                    const float4 x2 = __ldg(Xc + (int64_t)c2 * G);
-                    const float4 x3 = __ldg(Xc + (int64_t)c3 * G);
-                    fma4(acc, v0, x0); fma4(acc, v1, x1); fma4(acc, v2, x2); fma4(acc, v3, x3);
-                }
-                for (; i < e; i++) {
-                    const int c0 = __ldg(indices + i);
-                    const float v0 = HAS_VAL ? __ldg(vals + i) : 1.f;
-                    fma4(acc, v0, __ldg(Xc + (int64_t)c0 * G));
-                }
-                float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
-                if (HAS_SELF) {
-                    const float4 z = __ldg(Xself + row * G + c);
-                    r.x = fmaf(gamma, z.x, r.x); r.y = fmaf(gamma, z.y, r.y);
-                    r.z = fmaf(gamma, z.z, r.z); r.w = fmaf(gamma, z.w, r.w);
-                }
-                if (HAS_X0) {
-                    const float4 z = __ldg(X0 + row * G + c);
-                    r.x = fmaf(delta, z.x, r.x); r.y = fmaf(delta, z.y, r.y);
-                    r.z = fmaf(delta, z.z, r.z); r.w = fmaf(delta, z.w, r.w);
-                }
-                Y[row * G + c] = r;
-            }
+    if (has_push) {
+        for (int i2 = P.push_ptr[row], e2 = P.push_ptr[row + 1]; i2 < e2; i2++) {
+            const uint32_t d = P.push_dst[i2];
+            P.peer[d >> 29][(P.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + c] = r;
         }
     }
-}
-
-// Measured on B200 (SBM 1M / 20M, b = 80): v2 is SLOWER than v1 (0.73-0.84 ms vs 0.56 ms per sweep for tiles of
-// 256-2048 rows): halving the resident threads costs more than the L1 hits buy.  v1 stays the default;
-// GEMB_SPMM=v2 selects this kernel for experiments, GEMB_SPMM_TILE=<rows> sets its tile.
-// A third shape -- v1's 256-thread CTAs with SM-affine tile queues (%smid-keyed atomic counters, stealing) so that
-// the CTAs sharing an L1 work on neighbouring rows -- measured 0.76-0.84 ms per sweep and was removed.
-static int spmm_variant() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("GEMB_SPMM"); v = (e && e[0] == 'v' && e[1] >= '1' && e[1] <= '2') ? e[1] - '0' : 1; }
-    return v;
-}
-static int spmm_tile_rows() {
-    static int t = -1;
-    if (t < 0) { const char *e = getenv("GEMB_SPMM_TILE"); t = e ? atoi(e) : 512; if (t < 64) t = 64; }
-    return t;
 }
 
 int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha,
                 const float *X, const float *X0, float *Y) {
-    return spmm3_launch(ctx, A, n_rows, b, alpha, X, 0.f, nullptr, 1.f, X0, Y);
+    return spmm3_launch(ctx, A, n_rows, b, alpha, X, 0.f, nullptr, 1.f, X0, Y, nullptr);
 }
 
 int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha, const float *X,
-                 float gamma, const float *Xself, float delta, const float *X0, float *Y) {
+                 float gamma, const float *Xself, float delta, const float *X0, float *Y, const HaloPushArgs *push) {
     GEMB_ARG(b > 0 && b % 4 == 0 && b <= 1024, "block width must be a multiple of 4, <= 1024");
     if (n_rows == 0) return GEMB_OK;
     const int G = b / 4;
-    if (spmm_variant() == 2 && n_rows >= 65536 && G <= 256) {
-        if (!ctx->tile_counter) GEMB_CUDA(dmalloc(&ctx->tile_counter, sizeof(int)));
-        GEMB_CUDA(cudaMemsetAsync(ctx->tile_counter, 0, sizeof(int), ctx->stream));
-        const int groups = 1024 / G, tile_rows = spmm_tile_rows();
-        const int64_t tiles = (n_rows + tile_rows - 1) / tile_rows;
-        const int grid2 = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-        const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0, *XS4 = (const float4 *)Xself;
-        float4 *Y4 = (float4 *)Y;
-#define LAUNCH2(V, Z, S)                                                                                   \
-        spmm_tile_kernel<V, Z, S><<<grid2, 1024, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G, groups, \
-                                                                  tile_rows, alpha, gamma, delta, X4, XS4, X04, Y4, \
-                                                                  ctx->tile_counter)
-        const int sel2 = (A.data ? 4 : 0) | (X0 ? 2 : 0) | (Xself ? 1 : 0);
-        switch (sel2) {
-            case 0: LAUNCH2(false, false, false); break;
-            case 1: LAUNCH2(false, false, true); break;
-            case 2: LAUNCH2(false, true, false); break;
-            case 3: LAUNCH2(false, true, true); break;
-            case 4: LAUNCH2(true, false, false); break;
-            case 5: LAUNCH2(true, false, true); break;
-            case 6: LAUNCH2(true, true, false); break;
-            default: LAUNCH2(true, true, true); break;
-        }
-#undef LAUNCH2
-        GEMB_CUDA(cudaGetLastError());
-        count_launch();
-        return GEMB_OK;
-    }
     const int rows_per_cta = 256 / G;
     const int64_t grid = (n_rows + rows_per_cta - 1) / rows_per_cta;
     GEMB_ARG(grid < (int64_t)2147483647, "grid too large");
@@ -291,9 +200,18 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
     float4 *Y4 = (float4 *)Y;
     const bool heavy = A.n_items > 0 && G <= 256;
     const int heavy_deg = heavy ? SPMM_HEAVY_DEG : 0;
-#define LAUNCH(V, Z, S)                                                                              \
-    spmm_rowgroup_kernel<V, Z, S><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G,  \
-                                                            rows_per_cta, alpha, gamma, delta, X4, XS4, X04, Y4, heavy_deg)
+    HaloPushArgs PA;
+    memset(&PA, 0, sizeof PA);
+    if (push) PA = *push;
+#define LAUNCH(V, Z, S)                                                                                      \
+    do {                                                                                                     \
+        if (push)                                                                                            \
+            spmm_rowgroup_kernel<V, Z, S, true><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G, rows_per_cta,  \
+                                                                         alpha, gamma, delta, X4, XS4, X04, Y4, heavy_deg, PA); \
+        else                                                                                                 \
+            spmm_rowgroup_kernel<V, Z, S, false><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G, rows_per_cta, \
+                                                                          alpha, gamma, delta, X4, XS4, X04, Y4, heavy_deg, PA); \
+    } while (0)
     const int sel = (A.data ? 4 : 0) | (X0 ? 2 : 0) | (Xself ? 1 : 0);
     switch (sel) {
         case 0: LAUNCH(false, false, false); break;
@@ -326,7 +244,7 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
         GEMB_CUDA(cudaGetLastError());
         const int fgrid = (int)(((int64_t)A.n_heavy * G + 255) / 256);
 #define FIN(Z, S) spmm_heavy_finish_kernel<Z, S><<<fgrid, 256, 0, ctx->stream>>>(A.n_heavy, A.heavy_row, A.heavy_first, G, alpha, gamma, \
-                                                                               delta, P4, XS4, X04, Y4)
+                                                                               delta, P4, XS4, X04, Y4, push != nullptr, PA)
         if (X0 && Xself) FIN(true, true);
         else if (X0) FIN(true, false);
         else if (Xself) FIN(false, true);

@@ -28,6 +28,11 @@ def _true_csr(digraph, node_num):
     e = np.array([(int(u), int(v)) for u, v in digraph.edges()], dtype=np.int64).reshape(-1, 2)
     if e.size and (e.min() < 0 or e.max() >= node_num):
         raise ValueError('node ids must be 0..n-1 (the reference indexes the reconstruction by node id)')
+    if e.size and not digraph.is_directed():
+        # an nx.Graph lists every edge once, in one direction, but has_edge(i, j) (metrics.py:17) is true both ways
+        e = np.concatenate((e, e[e[:, 0] != e[:, 1]][:, ::-1]))
+    if e.size:
+        e = np.unique(e, axis=0)                       # rows sorted by (src, dst); MultiGraph duplicates dropped
     order = np.lexsort((e[:, 1], e[:, 0]))
     e = e[order]
     indptr = np.zeros(node_num + 1, dtype=np.int64)
@@ -93,6 +98,8 @@ def evaluateStaticGraphReconstruction(digraph, graph_embedding, X_stat, node_l=N
                     pos = np.empty(node_num, dtype=np.int64)
                     pos[np.array([int(u) for u in digraph.nodes], dtype=np.int64)] = np.arange(node_num)
                     ed = [(int(u), int(v), float(wt)) for u, v, wt in digraph.edges(data='weight', default=1)]
+                    if not digraph.is_directed():             # nx.to_numpy_matrix of an nx.Graph is symmetric
+                        ed = ed + [(v, u, wt) for u, v, wt in ed if u != v]
                     eu = np.array([t[0] for t in ed], dtype=np.int64)
                     ev = np.array([t[1] for t in ed], dtype=np.int64)
                     a = np.array([t[2] for t in ed], dtype=np.float64)

@@ -59,9 +59,10 @@ class HostCSR:
         return sp.csr_matrix((d, self.indices, self.indptr), shape=(self.n, self.n))
 
 
-def from_edges(n, src, dst, w=None, nodes=None, unit_if_all_ones=True):
+def from_edges(n, src, dst, w=None, nodes=None, unit_if_all_ones=True, dup='last'):
     """COO (row ids src, col ids dst in 0..n-1) -> CSR with sorted columns.  Duplicate (src, dst)
-    pairs keep the LAST weight (SNAP's AddEdge semantics; a DiGraph has none)."""
+    pairs keep the LAST weight (SNAP's AddEdge semantics; a DiGraph has none), or, with dup='sum', add up
+    (what nx.to_numpy_matrix does with the parallel edges of a MultiGraph)."""
     src = np.asarray(src, dtype=np.int64)
     dst = np.asarray(dst, dtype=np.int64)
     if src.size and (src.min() < 0 or dst.min() < 0 or src.max() >= n or dst.max() >= n):
@@ -76,11 +77,17 @@ def from_edges(n, src, dst, w=None, nodes=None, unit_if_all_ones=True):
         s, t = src[order], dst[order]
         ww = None if ww is None else ww[order]
     if s.size > 1:
-        dup = (s[1:] == s[:-1]) & (t[1:] == t[:-1])
-        if dup.any():
-            keep = np.concatenate((~dup, [True]))  # last of each run
-            s, t = s[keep], t[keep]
-            ww = None if ww is None else ww[keep]
+        dupm = (s[1:] == s[:-1]) & (t[1:] == t[:-1])
+        if dupm.any():
+            keep = np.concatenate((~dupm, [True]))  # last of each run
+            if dup == 'sum':
+                wsum = np.ones(s.size) if ww is None else ww
+                run = np.concatenate(([0], np.cumsum(~dupm)))          # run id of every entry
+                ww = np.bincount(run, weights=wsum)
+                s, t = s[keep], t[keep]
+            else:
+                s, t = s[keep], t[keep]
+                ww = None if ww is None else ww[keep]
     if ww is not None and unit_if_all_ones and np.all(ww == 1.0):
         ww = None
     indptr = np.zeros(n + 1, dtype=np.int64)
@@ -153,7 +160,7 @@ def from_networkx(graph, by_label=False):
     if not graph.is_directed() and not undirected_done:
         off = src != dst
         src, dst, w = np.concatenate((src, dst[off])), np.concatenate((dst, src[off])), np.concatenate((w, w[off]))
-    return from_edges(n, src, dst, w, nodes=nodes)
+    return from_edges(n, src, dst, w, nodes=nodes, dup='sum' if graph.is_multigraph() else 'last')
 
 
 def n2v_inputs_from_networkx(graph):

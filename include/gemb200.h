@@ -118,10 +118,19 @@ typedef struct {
     uint64_t seed;         /* start block, default 1234 */
     int32_t compute_residual; /* 1: one extra Katz application to report ||S^T u - sigma v|| */
     int32_t verbose;
-    int32_t algorithm;     /* 0 = auto (2 when the shard is symmetric, else 1); 1 = subspace iteration on
-                              S^T S through Katz sweeps (any A); 2 = Chebyshev-filtered subspace iteration on
-                              A itself, S = f(A) (symmetric A only) */
+    int32_t algorithm;     /* 0 = auto (symmetric shard: 2, or 3 when the first Rayleigh-Ritz round shows a skewed
+                              spectrum; else 1); 1 = subspace iteration on S^T S through Katz sweeps (any A);
+                              2 = Chebyshev-filtered subspace iteration on A itself, S = f(A) (symmetric A only);
+                              3 = thick-restart block Lanczos on A (symmetric A only; power-law spectra) */
     int32_t cheb_degree;   /* filter degree per outer iteration of algorithm 2, default 8 */
+    float cheb_range_log2; /* algorithm 2: the filter degree is lowered until the filtered block's column dynamic range
+                              T_m(x_L) stays below 2^cheb_range_log2 (fp32 Gram-based orthonormalisation squares it);
+                              0 = default (8) */
+    int32_t stop_rule;     /* 0 = relative change of every singular value <= tol (default);
+                              1 = residual: max_j ||S v_j - sigma_j u_j|| / sigma_max <= tol over the top k, estimated
+                                  from the Rayleigh-Ritz products (algorithm 2: |f'(l_j)| ||A v_j - l_j v_j||) */
+    int32_t algorithm3_basis; /* algorithm 3 (thick-restart block Lanczos on A, symmetric A): maximum basis width,
+                              0 = default (max(2k + 64, 192) rounded to the block) */
 } gemb_hope_opts;
 
 typedef struct {
@@ -142,12 +151,29 @@ typedef struct {
     float norm2_A;         /* estimated ||A||_2 */
     float ritz_change;     /* last max relative Ritz-value change */
     float resid_max;       /* max_j ||S^T u_j - sigma_j v_j|| / sigma_max (compute_residual=1) */
+    float resid_est;       /* stop_rule = 1: the residual estimate the last round stopped on (else -1) */
+    int32_t mg_mode;       /* 0 = single GPU; 1 = all-gather of the block per sweep; 2 = needed-rows-only exchange over
+                              NVLink peer memory (CUDA IPC): rows are stored into the peers' halo slots by the kernel
+                              that produces them */
+    int64_t halo_rows;     /* mg_mode 2: distinct remote rows this shard references */
+    int64_t push_rows;     /* mg_mode 2: (row, peer) pairs this rank stores per exchanged block */
+    int64_t pushes;        /* mg_mode 2: blocks exchanged in this call (NVLink bytes out = pushes*push_rows*4*block) */
 } gemb_hope_stats;
 
 /* X_out: n_local x d host buffer, or NULL to leave the result on the device (bench `value`).
  * sigma_out: d/2 floats (ascending) or NULL. */
 int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts *opts, float *X_out,
               float *sigma_out, gemb_hope_stats *stats);
+
+/* The diagnostic hope.py:38-40 prints: || U diag(s) V^T - S ||_F = || X1 X2^T - S ||_F with S = (I - beta A)^-1 beta A.
+ * X: host, n x d row-major fp32 (the embedding gemb_hope returned).  S is never stored whole:
+ *   n_probe <= 0 : exact -- S is applied to the identity in column panels (n sweeps' worth of work: meant for
+ *                  n <= ~10^4, the sizes at which the reference can run at all);
+ *   n_probe  > 0 : Hutchinson estimate sqrt(mean_j ||(X1 X2^T - S) z_j||^2) over n_probe Rademacher vectors
+ *                  (SURVEY H8), relative standard error ~ sqrt(2 / n_probe).
+ * Single GPU (the graph uploaded with row0 = 0, n_local = n). */
+int gemb_hope_svd_error(gemb_graph *g, int d, float beta, const float *X, int n_probe, uint64_t seed,
+                        double *err_out);
 
 /* ---- node2vec.  Replaces the SNAP executable GEM shells out to (node2vec.py:31-48):
  * PreprocessTransitionProbs (bin@0x4127f0), node2vec() walks (bin@0x40c420),

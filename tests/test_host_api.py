@@ -165,3 +165,38 @@ def test_synthetic_generators_match_the_survey_configs():
     per_u = np.array([u.indptr[(p + 1) * per] - u.indptr[p * per] for p in range(8)])
     assert per_u.max() > 2.0 * per_u.mean()                                  # without it rank 0 owns the hubs
     assert np.array_equal(np.sort(np.diff(u.indptr)), np.sort(deg))          # same graph up to relabelling
+
+
+def test_scipy_inputs_get_past_the_empty_graph_guard():
+    """scipy sparse matrices AND arrays raise TypeError from len(); the guard must look at .shape first."""
+    import scipy.sparse as sp
+    from gem_b200.embedding.hope import HOPE, _graph_is_empty
+    from gem_b200.graph import HostCSR
+    A = sp.random(12, 12, 0.3, format='csr', random_state=0)
+    for M in (A, sp.csr_array(A), sp.coo_matrix(A)):
+        assert not _graph_is_empty(M)
+        csr = HOPE(d=4, beta=0.01)._to_csr(M)
+        assert isinstance(csr, HostCSR) and csr.n == 12 and csr.nnz == A.nnz
+    assert _graph_is_empty(sp.csr_matrix((0, 0))) and _graph_is_empty(None)
+    import networkx as nx
+    assert _graph_is_empty(nx.DiGraph()) and not _graph_is_empty(nx.path_graph(3))
+    with pytest.raises(ValueError, match='graph needed'):
+        HOPE(d=4, beta=0.01).learn_embedding(graph=sp.csr_matrix((0, 0)))
+
+
+def test_multigraph_parallel_edges_are_summed_like_to_numpy_matrix():
+    import networkx as nx
+    from gem_b200 import graph as hg
+    M = nx.MultiDiGraph()
+    M.add_edge(0, 1, weight=2.0); M.add_edge(0, 1, weight=3.0); M.add_edge(1, 2); M.add_edge(1, 2); M.add_edge(2, 0)
+    assert np.array_equal(hg.from_networkx(M).to_scipy().toarray(), nx.to_numpy_array(M))
+
+
+def test_device_graph_refuses_offsets_beyond_int32():
+    from gem_b200 import _native
+
+    class FakeCtx:
+        _h = None
+    ip = np.array([0, 2 ** 31], dtype=np.int64)
+    with pytest.raises(ValueError, match='int32 offsets'):
+        _native.DeviceGraph(FakeCtx(), 1, ip, np.zeros(1, np.int32))

@@ -61,3 +61,40 @@ def test_random_edge_pairs_contract():
     assert len(s) == len(p) and not any((b, a) in s for a, b in p if a != b)
     assert get_random_edge_pairs(50, 0.1, True, seed=3) == p
     assert len(get_random_edge_pairs(50, 0.1, False, seed=3)) == int(0.1 * 50 * 49)
+
+
+@pytest.mark.parametrize('name', ['eval_karate_hope', 'eval_karate_n2v', 'eval_randw200_split', 'eval_randw200_dot'])
+def test_reference_named_entry_points(eval_oracle, name):
+    """computeMAP / computePrecisionCurve / get_edge_list_from_adj_mtrx under the reference's names
+    (gem/evaluation/metrics.py:6-46, gem/utils/evaluation_util.py:20-36) reproduce the reference goldens."""
+    import networkx as nx
+    from gem_b200.evaluation import metrics
+    from gem_b200.utils import evaluation_util
+    z, n, _ = eval_golden(name)
+    adj = eval_oracle.reconstruct(z['X'], bool(z['split']))
+    G = nx.DiGraph()
+    G.add_nodes_from(int(x) for x in z['nodes'])
+    G.add_weighted_edges_from((int(a), int(b), float(c)) for a, b, c in z['edges'])
+    for tag, und in (('und', True), ('dir', False)):
+        el = evaluation_util.get_edge_list_from_adj_mtrx(adj, is_undirected=und)
+        assert len(el) == int(z[tag + '_n_pred'])
+        assert abs(metrics.computeMAP(el, G, is_undirected=und) - float(z[tag + '_MAP'])) < 1e-13
+        prec, delta = metrics.computePrecisionCurve(el, G)
+        assert np.array_equal(np.array(prec[:4096]), z[tag + '_prec_head'])
+        p10, _ = metrics.computePrecisionCurve(el, G, max_k=10)
+        assert p10 == prec[:10]
+    pairs = [(0, 1), (3, 2), (5, 5)]
+    got = evaluation_util.get_edge_list_from_adj_mtrx(adj, threshold=-1e9, edge_pairs=pairs)
+    assert [(a, b) for a, b, _ in got] == pairs and got[1][2] == adj[3, 2]
+
+
+def test_true_csr_of_an_undirected_graph_has_both_directions():
+    """an nx.Graph stores (5, 2) once, but has_edge(2, 5) is True in the reference (metrics.py:17)."""
+    import networkx as nx
+    from gem_b200.evaluation.evaluate_graph_reconstruction import _true_csr
+    G = nx.Graph()
+    G.add_nodes_from(range(6))
+    G.add_edges_from([(5, 2), (0, 1), (3, 3)])
+    indptr, indices = _true_csr(G, 6)
+    rows = np.repeat(np.arange(6), np.diff(indptr))
+    assert sorted(zip(rows.tolist(), indices.tolist())) == [(0, 1), (1, 0), (2, 5), (3, 3), (5, 2)]
