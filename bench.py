@@ -12,7 +12,9 @@ the graph.
   e2e   : the same metric through the reference-facing plugin call HOPE.learn_embedding(graph=CSR)
           with HOST buffers: pinned CSR -> H2D, solve, D2H of the n x d embedding, every step.
   N > 1 : launched by torchrun, one rank per GPU; weak scaling: n = N * 1,000,000 (rows per GPU fixed),
-          CSR row-sharded, all-gather of the Krylov block per SpMM + b x b all-reduce per Gram (NCCL).
+          CSR row-sharded; only the rows a shard references travel, stored into the peers' halo slots over NVLink by the
+          kernel that produces them (gem_b200/csrc/halo.cu); b x b all-reduce per Gram on NCCL.
+  The default line also carries a "node2vec" sub-record: BASELINE.json configs[2] on the same graph (one epoch).
 --workload node2vec: BASELINE.json configs[2] (d=128, p=q=1, 10 walks x 80, context 10, 1 epoch).
 --workload recon: the step after learn_embedding in every reference test (tests/fit_model.py:10):
   evaluateStaticGraphReconstruction of a HOPE embedding (d=128) of an SBM with --recon-n nodes (default 32768):
@@ -20,8 +22,9 @@ the graph.
   per second (n^2 / step time; the work is quadratic, so nodes/s would depend on n).
 --impl reference: the reference's CPU implementation of the same path on the host cores
   (HOPE: oracle/hope_oracle.hope_sparse = scipy svds over the matrix-free Katz operator, the only
-  form of hope.py:28-36 that fits in memory beyond ~50k nodes; node2vec: the reference's own SNAP
-  binary from oracle/_ref when present, else oracle/n2v_oracle.c), on a bounded sample.
+  form of hope.py:28-36 that fits in memory beyond ~50k nodes, at the FULL 1M-node configuration with the operator on
+  all host cores; node2vec: the reference's own SNAP binary from oracle/_ref when present, else
+  oracle/n2v_oracle.c, on a bounded sample).
 """
 import argparse
 import json
@@ -142,18 +145,29 @@ def dist_sum(dist, x, local):
 
 
 # ----------------------------------------------------------------------------------- CPU baselines
-def cpu_hope_sample(n_sample, d, beta, tol, seed=42):
-    """The reference path on the host: scipy svds (hope.py:33) over the Katz operator (hope.py:29-31,
-    applied matrix-free).  Returns nodes/s."""
+def cpu_hope_sample(n_sample, d, beta, tol, seed=42, A=None):
+    """The reference path on the host: scipy svds (hope.py:33, ARPACK) over the Katz operator (hope.py:29-31) applied
+    matrix-free in fp64, the operator's row loop on all host cores (oracle/katz_omp.c), ARPACK's own BLAS calls on
+    whatever threads the BLAS takes.  Returns (nodes/s, seconds, info)."""
     sys.path.insert(0, os.path.join(REPO, 'oracle'))
     import hope_oracle as ho
     from gem_b200 import synth
-    csr = synth.sbm(n=n_sample, block=min(1000, n_sample), seed=seed)
-    A = csr.to_scipy()
+    if A is None:
+        A = synth.sbm(n=n_sample, block=min(1000, n_sample), seed=seed).to_scipy()
     t = time.perf_counter()
-    X, s, info = ho.hope_sparse(A, d, beta, katz_tol=1e-7, tol=tol)
+    X, s, info = ho.hope_sparse(A, d, beta, katz_tol=1e-7, tol=tol, threads=True)
     dt = time.perf_counter() - t
-    return n_sample / dt, dt, info
+    info['threads'] = int(ho.katz_omp_lib().katz_omp_threads())
+    return A.shape[0] / dt, dt, info
+
+
+# The UNMODIFIED reference class (gem.embedding.hope.HOPE: dense inverse + scipy svds) cannot travel to the GPU box
+# (/root/reference does not exist there) and cannot hold more than ~16k nodes anywhere (n x n fp64).  These are its wall
+# times on the same SBM family at d = 128, beta = 0.01, measured in the build container (8 cores) with the harness-side
+# networkx shim (DESIGN.md section 6); printed beside the reference arm for orientation, never used in a ratio.
+REFERENCE_CLASS_TIMINGS = {'where': 'build container, 8 host cores, gem.embedding.hope.HOPE unmodified',
+                           'n=1024': {'seconds': 1.9, 'nodes_per_s': 551}, 'n=2048': {'seconds': 1.7, 'nodes_per_s': 1184},
+                           'n=4096': {'seconds': 11.4, 'nodes_per_s': 360}, 'n=8192': {'seconds': 53.6, 'nodes_per_s': 153}}
 
 
 def cpu_n2v_sample(n_sample, d, walk_len, num_walks, con_size, threads):
@@ -234,18 +248,27 @@ def run_reference(args):
         return max(floor, int(base_nodes * min(1.0, 150.0 / (max(args.steps, 1) * base_seconds))))
 
     if args.workload == 'hope':
-        n_s = bounded(50000, 40.0, 8000) // 1000 * 1000
-        vals, secs = [], []
-        for _ in range(args.warmup):
-            cpu_hope_sample(n_s, args.d, args.beta, HOPE_SOLVER['tol'])
-        for _ in range(args.steps):
-            v, dt, info = cpu_hope_sample(n_s, args.d, args.beta, HOPE_SOLVER['tol'])
-            vals.append(v); secs.append(dt)
+        # the SAME configuration as our arm: n = args.n (1M) nodes, same generator and seed.  One solve takes minutes, so
+        # the K requested steps are run only while a ~9 minute budget lasts (at least one); --cpu-sample N shrinks the graph.
+        from gem_b200 import synth
+        n_s = args.cpu_sample or args.n
+        A = synth.sbm(n=n_s, block=min(1000, n_s), seed=42).to_scipy()
+        secs, info = [], None
+        budget_s = float(os.environ.get('GEMB_REF_BUDGET_S', '540'))
+        t_begin = time.perf_counter()
+        for i in range(args.steps):
+            v, dt, info = cpu_hope_sample(n_s, args.d, args.beta, HOPE_SOLVER['tol'], A=A)
+            secs.append(dt)
+            if time.perf_counter() - t_begin + dt > budget_s:
+                break
         value = n_s * len(secs) / sum(secs)
-        kind, used = 'port', 1
-        sample = ('SBM n=%d (same density, seed 42), d=%d, beta=%g, scipy svds(tol=%g, ARPACK) over the matrix-free '
-                  'Katz operator, J=%d Horner terms' % (n_s, args.d, args.beta, HOPE_SOLVER['tol'], info['katz_terms']))
-        cfg = {'workload': 'HOPE d=%d beta=%g, SBM 1M nodes / 20M edges (CPU arm runs a bounded sample)' % (args.d, args.beta)}
+        kind, used = 'port', info['threads']
+        sample = ('the full workload: SBM n=%d (seed 42), d=%d, beta=%g; scipy svds(tol=%g, ARPACK) over the matrix-free '
+                  'fp64 Katz operator (J=%d Horner terms, %d SpMVs per solve) with the operator on %d OpenMP threads; '
+                  '%d of the %d requested steps timed (each a complete solve), no warm-up' % (
+                      n_s, args.d, args.beta, HOPE_SOLVER['tol'], info['katz_terms'], info['spmv'], used, len(secs), args.steps))
+        cfg = {'workload': hope_workload_name(args.d, args.beta, n_s, 1), 'timed_solves': len(secs),
+               'reference_class_itself': REFERENCE_CLASS_TIMINGS}
     else:
         n_s = bounded(4000, 65.0, 500)
         n_s = n_s // 1000 * 1000 if n_s >= 1000 else n_s // 100 * 100      # synth.sbm wants whole blocks
@@ -261,7 +284,8 @@ def run_reference(args):
         cfg = {'workload': 'node2vec d=%d p=q=1 r=%d l=%d k=%d, SBM 1M nodes / 20M edges (CPU arm runs a bounded sample)' % (
             args.d, args.num_walks, args.walk_len, args.con_size)}
     line = {'impl': 'reference', 'metric': 'nodes/sec embedded at d=128', 'value': value, 'unit': 'nodes/s',
-            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup_requested,
+            'warmup_done': 0 if args.workload == 'hope' else args.warmup, 'steps_done': len(secs),
             'ms_per_step': 1e3 * sum(secs) / len(secs), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
             'cpu_baseline': {'value': value, 'unit': 'nodes/s', 'cores': used, 'kind': kind, 'sample': sample,
@@ -271,6 +295,49 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------- our arm
+def hope_workload_name(d, beta, n, world):
+    return ('HOPE d=%d beta=%g on SBM n=%d (%d per GPU), ~20 directed edges per node, 1000-node blocks, '
+            'deg 16 in / 4 out, seed 42' % (d, beta, n, n // world))
+
+
+def fp64_accuracy_of_solution(csr, X, sigma, beta, n_sample=8, katz_terms=14):
+    """Accuracy of the solution the timed solver setting produces, measured against the fp64 Katz operator on the host
+    (plain scipy.sparse, no oracle code): for n_sample of the k triplets (always the largest one)
+        resid   = max(||S v - sigma u||, ||S^T u - sigma v||) / sigma_max
+        sigma   = |u^T S v - sigma| / sigma          (Rayleigh quotient of the pair vs the value the solver reports)
+    and the angle between the solver's top right vector and the dominant eigenvector of A from 60 fp64 power steps
+    (S = f(A) shares A's eigenvectors; the top one is isolated on the SBM, so this angle is well defined)."""
+    import scipy.sparse as sp
+    n, d = X.shape
+    k = d // 2
+    A = sp.csr_matrix((np.ones(csr.nnz), csr.indices, np.asarray(csr.indptr, dtype=np.int64)), shape=(n, n))
+    sig = np.asarray(sigma, dtype=np.float64)
+    cols = sorted(set([k - 1] + list(np.linspace(0, k - 1, n_sample).astype(int))))
+    rs = np.sqrt(np.maximum(sig[cols], 1e-300))
+    U = X[:, cols].astype(np.float64) / rs
+    V = X[:, [k + c for c in cols]].astype(np.float64) / rs
+
+    def katz(M, B):
+        W = B
+        for _ in range(katz_terms - 1):
+            W = B + beta * (M @ W)
+        return beta * (M @ W)
+    SV, STU = katz(A, V), katz(A.T.tocsr(), U)
+    smax = float(sig.max())
+    r1 = np.linalg.norm(SV - U * sig[cols], axis=0) / smax
+    r2 = np.linalg.norm(STU - V * sig[cols], axis=0) / smax
+    rq = np.abs(np.sum(U * SV, axis=0) - sig[cols]) / sig[cols]
+    x = np.ones(n) / np.sqrt(n)
+    for _ in range(60):
+        x = A @ x
+        x /= np.linalg.norm(x)
+    vt = V[:, cols.index(k - 1)]
+    cosang = min(1.0, abs(float(vt @ x)) / float(np.linalg.norm(vt)))
+    return {'triplets_checked': len(cols), 'resid_max_rel_sigma_max_fp64': float(max(r1.max(), r2.max())),
+            'sigma_rel_err_vs_rayleigh_fp64': float(rq.max()), 'top1_angle_deg_vs_fp64_power_iteration': float(np.degrees(np.arccos(cosang))),
+            'orthonormality_max_abs': float(max(np.abs(U.T @ U - np.eye(len(cols))).max(), np.abs(V.T @ V - np.eye(len(cols))).max()))}
+
+
 def pinned_csr(csr):
     """Copy of the CSR in pinned host memory with int32 offsets (what gemb_graph_upload reads)."""
     from gem_b200 import _native
@@ -315,7 +382,7 @@ def run_hope(args, dist, rank, world, local):
     for _ in range(args.steps):
         _, _, st = g.hope(args.d, args.beta, want_output=False, **solver)
         dev_ms += st['total_ms']
-        stats = st if stats is None else {k: (stats[k] + st[k] if k in ('spmm_ms', 'dense_ms', 'comm_ms', 'spmm_count') else st[k])
+        stats = st if stats is None else {k: (stats[k] + st[k] if k in ('spmm_ms', 'dense_ms', 'comm_ms', 'spmm_count', 'pushes') else st[k])
                                           for k in st}
     dist_barrier(dist, local)
     wall_s = time.perf_counter() - t0
@@ -350,66 +417,95 @@ def run_hope(args, dist, rank, world, local):
                 'launches_per_step': stats['spmm_count'] / args.steps,
                 'share_of_step': stats['spmm_ms'] / max(dev_ms, 1e-9)}
 
-    # e2e through the plugin class with host buffers (rank-local shard in multi-GPU is not exposed by
-    # the plugin: e2e is measured at N=1 only)
+    # e2e through the plugin class with host buffers.  N > 1: the SPMD contract of the plugin -- every
+    # rank calls learn_embedding under the initialised process group with the graph in pinned host memory, uploads ITS
+    # row shard, and reads back ITS rows of X; the step time is the max over ranks of the host clock around the call.
     e2e = None
-    if world == 1 and not args.no_e2e:
+    accuracy = None
+    if not args.no_e2e:
+        g.free()
+        g = None
         hc = pinned_csr(csr)
-        out = _native.pinned_empty((csr.n, args.d), np.float32)
+        n_own = len(csr.row_shard(rank, world)[1]) - 1
+        out = _native.pinned_empty((n_own, args.d), np.float32)
         HOPE.hyper_params.clear(); HOPE.hyper_params.update({'method_name': 'hope_gsvd'})
-        model = HOPE(d=args.d, beta=args.beta, device=local, **solver)
+        model = HOPE(d=args.d, beta=args.beta, device=local, svd_error_probes=False, **solver)
         model.learn_embedding(graph=hc, out=out)                      # warm-up
         # K plugin calls, each timed on the host clock around the whole call (H2D of the CSR, solve, D2H of X).
         # The GPU boxes show bursts of host-side stalls (a 9 ms D2H wait returning after 600 ms, with the device
         # idle) that have nothing to do with this process, so the reported step time is the MEDIAN call; the
         # mean, min and max are given beside it.
-        ksteps = max(3, args.steps)
+        ksteps = max(3, args.steps) if world == 1 else max(3, min(args.steps, 5))
         step_ms = []
         for _ in range(ksteps):
+            dist_barrier(dist, local)
             t0 = time.perf_counter()
             X = model.learn_embedding(graph=hc, is_weighted=True, no_python=True, out=out)
             _ = float(X[0, 0])
-            step_ms.append((time.perf_counter() - t0) * 1e3)
+            step_ms.append(dist_max(dist, (time.perf_counter() - t0) * 1e3, local))
         e2e_s = float(np.median(step_ms)) * 1e-3
         e2e = {'value': csr.n / e2e_s, 'unit': 'nodes/s', 'ms_per_step': e2e_s * 1e3, 'stat': 'median of %d calls' % ksteps,
                'mean_ms_per_step': float(np.mean(step_ms)), 'min_ms_per_step': float(np.min(step_ms)),
-               'max_ms_per_step': float(np.max(step_ms)),
-               'h2d_bytes_per_step': int(hc.indptr.nbytes + hc.indices.nbytes),
+               'max_ms_per_step': float(np.max(step_ms)), 'value_from_mean': csr.n / (float(np.mean(step_ms)) * 1e-3),
+               'h2d_bytes_per_step': int(4 * (n_own + 1) + 4 * int(csr.indptr[min(csr.n, (rank + 1) * ((csr.n + world - 1) // world))]
+                                                                  - csr.indptr[rank * ((csr.n + world - 1) // world)])),
                'd2h_bytes_per_step': int(out.nbytes + 4 * (args.d // 2)), 'steps': ksteps,
-               'call': 'gem_b200.embedding.hope.HOPE(d, beta).learn_embedding(graph=<CSR in pinned host memory>)'}
+               'per_call_setup_included': 'ctx + (N>1) NCCL communicator, halo plan, IPC mapping of the work blocks' if world > 1 else 'ctx',
+               'call': 'gem_b200.embedding.hope.HOPE(d, beta).learn_embedding(graph=<CSR in pinned host memory>)'
+                       + (' on every rank (SPMD, rows of X per rank)' if world > 1 else '')}
+        if world == 1 and not args.no_accuracy:
+            accuracy = fp64_accuracy_of_solution(csr, np.asarray(X), model._sigma, args.beta)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        n_s = args.cpu_sample or 50000
+        n_s = args.cpu_sample or 100000
         v, dt, info = cpu_hope_sample(n_s, args.d, args.beta, solver['tol'])
-        cpu = {'value': v, 'unit': 'nodes/s', 'cores': 1, 'kind': 'port', 'host_cores': os.cpu_count(),
+        cpu = {'value': v, 'unit': 'nodes/s', 'cores': info['threads'], 'kind': 'port', 'host_cores': os.cpu_count(),
                'seconds': dt,
-               'sample': 'SBM n=%d (same density, seed 42), d=%d, beta=%g: scipy svds(tol=%g) over the matrix-free Katz '
-                         'operator (oracle/hope_oracle.hope_sparse), J=%d, %d SpMVs' % (
-                             n_s, args.d, args.beta, solver['tol'], info['katz_terms'], info['spmv'])}
-    g.free()
+               'sample': 'SBM n=%d (same density, seed 42), d=%d, beta=%g: scipy svds(tol=%g, ARPACK) over the matrix-free fp64 '
+                         'Katz operator (oracle/hope_oracle.hope_sparse, operator on %d OpenMP threads), J=%d, %d SpMVs; the '
+                         'full 1M-node solve is what `--impl reference` times' % (
+                             n_s, args.d, args.beta, solver['tol'], info['threads'], info['katz_terms'], info['spmv'])}
+    if g is not None:
+        g.free()
+    line = None
     if rank == 0:
+        mg = {0: 'single GPU', 1: 'row-sharded CSR x%d, ncclAllGather of the block per SpMM' % world,
+              2: 'row-sharded CSR x%d; needed rows only, stored into the peers\' halo slots over NVLink (CUDA IPC) by the '
+                 'producing kernel; b x b Gram all-reduce on NCCL' % world}[stats.get('mg_mode', 0)]
         line = {'metric': 'nodes/sec embedded at d=128', 'value': value, 'unit': 'nodes/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                 'data': 'synthetic',
-                'config': {'workload': 'HOPE d=%d beta=%g on SBM n=%d (%d per GPU), nnz=%d directed, 1000-node blocks, '
-                                       'deg 16 in / 4 out, seed 42' % (args.d, args.beta, n, args.n, csr.nnz),
+                'config': {'workload': hope_workload_name(args.d, args.beta, n, world), 'nnz': csr.nnz,
                            'solver': dict(solver, block=stats['block'], katz_terms=stats['katz_terms'],
                                           iters=stats['iters'], converged=stats['converged'],
                                           ritz_change=stats['ritz_change'], resid_max_rel_sigma_max=resid_max,
+                                          accuracy_vs_fp64=accuracy,
                                           algorithm={1: 'subspace iteration on S^T S (Katz sweeps)',
-                                                     2: 'Chebyshev-filtered subspace iteration on A (S = f(A), A symmetric)'}
+                                                     2: 'Chebyshev-filtered subspace iteration on A (S = f(A), A symmetric)',
+                                                     3: 'thick-restart block Lanczos on A (S = f(A), A symmetric)'}
                                           .get(stats['algorithm'], stats['algorithm'])),
-                           'parallelism': 'row-sharded CSR x%d, all-gather per SpMM' % world if world > 1 else 'single GPU',
+                           'parallelism': mg,
+                           'exchange': None if world == 1 else {'halo_rows_rank0': stats.get('halo_rows'), 'push_rows_rank0': stats.get('push_rows'),
+                                                                'blocks_exchanged_per_step': stats.get('pushes', 0) / args.steps,
+                                                                'nvlink_bytes_out_per_step_rank0': stats.get('pushes', 0) / args.steps * stats.get('push_rows', 0) * 4 * stats['block']},
                            'l2_policy': 'inputs larger than L2 (CSR %.0f MB + 5 blocks of %.0f MB vs 126 MB L2)' % (
                                (csr.nnz * 4 + csr.n * 4) / 1e6, csr.n * stats['block'] * 4 / 1e6 / world)},
                 'wall_ms_per_step': wall_s * 1e3 / args.steps, 'graph_gen_s': gen_s,
                 'phases_ms_per_step': {'spmm': stats['spmm_ms'] / args.steps, 'dense': stats['dense_ms'] / args.steps,
                                        'comm': stats['comm_ms'] / args.steps},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu}
-        print(json.dumps(line), flush=True)
     ctx.close()
+    return line
+
+
+def n2v_traffic():
+    tp = os.path.join(REPO, 'profiles', 'sgns_traffic.json')
+    try:
+        return json.load(open(tp)).get('dram_bytes_per_launch')
+    except Exception:
+        return None
 
 
 def run_node2vec(args, dist, rank, world, local):
@@ -448,7 +544,7 @@ def run_node2vec(args, dist, rank, world, local):
     sg_bytes = pairs * 14 * 4 * args.d
     achieved = sg_bytes / world / (agg['sgns_ms'] * 1e-3) / 1e9 if agg['sgns_ms'] > 0 else 0.0
     roofline = {'kernel': 'sgns (warp per walk, fp32 tables)', 'bound': 'hbm', 'achieved': achieved,
-                'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+                'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': n2v_traffic(),
                 'peak_source': peak_src, 'bytes_per_launch': sg_bytes / world / args.steps,
                 'ms_per_launch': agg['sgns_ms'] / args.steps, 'share_of_step': agg['sgns_ms'] / max(dev_ms, 1e-9),
                 'note': 'algorithmic bytes = 7168 B per (centre, context) pair (SURVEY 8(d)); rows of the walk and the '
@@ -468,13 +564,14 @@ def run_node2vec(args, dist, rank, world, local):
                'call': 'gem_b200.embedding.node2vec.node2vec(...).learn_embedding(graph=(CSR, node table))'}
     cpu = None
     if rank == 0 and not args.no_cpu:
-        n_s = args.cpu_sample or 4000
+        n_s = args.n2v_cpu_sample or 2000
         v, dt, kind, used = cpu_n2v_sample(n_s, args.d, args.walk_len, args.num_walks, args.con_size, os.cpu_count() or 1)
         cpu = {'value': v, 'unit': 'nodes/s', 'cores': used, 'kind': kind, 'host_cores': os.cpu_count(), 'seconds': dt,
                'sample': 'SBM n=%d (same density, seed 42), d=%d r=%d l=%d k=%d e=1 p=q=1 (%s)' % (
                    n_s, args.d, args.num_walks, args.walk_len, args.con_size,
                    'gem/c_exe/node2vec, OMP threads = cores' if kind == 'reference' else 'oracle/n2v_oracle.c, 1 thread')}
     g.free()
+    line = None
     if rank == 0:
         line = {'metric': 'nodes/sec embedded at d=128', 'value': value, 'unit': 'nodes/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
@@ -486,8 +583,8 @@ def run_node2vec(args, dist, rank, world, local):
                                csr.n * args.d * 4 // 10**6, csr.n * args.num_walks * args.walk_len * 4 // 10**6)},
                 'phases_ms_per_step': {k: agg[k] / args.steps for k in ('alias_ms', 'shuffle_ms', 'walk_ms', 'vocab_ms', 'sgns_ms', 'comm_ms')},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu}
-        print(json.dumps(line), flush=True)
     ctx.close()
+    return line if rank == 0 else None
 
 
 def run_recon(args, dist, rank, world, local):
@@ -600,23 +697,41 @@ def main():
     ap.add_argument('--con-size', type=int, default=10)
     ap.add_argument('--recon-n', type=int, default=32768, help='nodes of the reconstruction workload')
     ap.add_argument('--cpu-sample', type=int, default=None, help='nodes in the CPU baseline sample')
+    ap.add_argument('--n2v-cpu-sample', type=int, default=None, help='nodes in the node2vec CPU baseline sample')
+    ap.add_argument('--no-node2vec', action='store_true', help='HOPE line without the node2vec sub-record')
+    ap.add_argument('--no-accuracy', action='store_true', help='skip the fp64 host check of the timed solution')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     if args.steps is None:
         args.steps = {'hope': 5, 'recon': 5}.get(args.workload, 1)
     if args.impl == 'reference':
-        args.warmup = min(args.warmup, 1)      # each CPU step is a bounded 10-30 s sample
+        args.warmup_requested = args.warmup
+        args.warmup = min(args.warmup, 1)      # each CPU step is a bounded 10-30 s sample (HOPE: a full solve, no warm-up)
         run_reference(args)
         return
     dist, rank, world, local = dist_setup(args.gpus)
     try:
         if args.workload == 'hope':
-            run_hope(args, dist, rank, world, local)
+            line = run_hope(args, dist, rank, world, local)
+            if not args.no_node2vec:
+                # BASELINE.json configs[2] rides in the same line (one epoch = one step; it takes ~10 s, so it is timed
+                # once whatever --steps says): the driver's bench and scaling runs then see node2vec too
+                steps, warm = args.steps, args.warmup
+                args.steps, args.warmup = 1, min(args.warmup, 3)
+                sub = run_node2vec(args, dist, rank, world, local)
+                args.steps, args.warmup = steps, warm
+                if line is not None:
+                    line['node2vec'] = sub
+                    line['gpu_launches'] += sub['gpu_launches']
+            if line is not None:
+                print(json.dumps(line), flush=True)
         elif args.workload == 'recon':
             run_recon(args, dist, rank, world, local)
         else:
-            run_node2vec(args, dist, rank, world, local)
+            line = run_node2vec(args, dist, rank, world, local)
+            if line is not None:
+                print(json.dumps(line), flush=True)
     finally:
         if dist is not None:
             dist.destroy_process_group()

@@ -100,20 +100,81 @@ def hope_dense_lapack(A, d, beta):
     return _embed_from_svd(u, s, vt), s
 
 
-def hope_sparse(A, d, beta, katz_tol=1e-12, terms=None, tol=0, maxiter=None, rng=0, ncv=None):
+_katz_lib = None
+
+
+def katz_omp_lib():
+    """oracle/build/libkatz_omp.so (OpenMP Katz operator, same arithmetic as katz_apply), built on demand."""
+    global _katz_lib
+    if _katz_lib is None:
+        import ctypes
+        import os
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        so = os.path.join(here, 'build', 'libkatz_omp.so')
+        src = os.path.join(here, 'katz_omp.c')
+        if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src)):
+            subprocess.check_call(['make', '-C', here, 'build/libkatz_omp.so'], stdout=subprocess.DEVNULL)
+        L = ctypes.CDLL(so)
+        i64p = np.ctypeslib.ndpointer(np.int64, flags='C')
+        i32p = np.ctypeslib.ndpointer(np.int32, flags='C')
+        f64p = np.ctypeslib.ndpointer(np.float64, flags='C')
+        L.katz_apply_omp.argtypes = [ctypes.c_int64, i64p, i32p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int,
+                                     ctypes.c_int, f64p, f64p, f64p, f64p]
+        L.katz_omp_threads.restype = ctypes.c_int
+        _katz_lib = L
+    return _katz_lib
+
+
+class KatzOMP:
+    """x -> sum_{j=1..J} (beta M)^j x for a fixed CSR M (fp64), rows spread over the host cores."""
+
+    def __init__(self, M, beta, J):
+        M = sp.csr_matrix(M, dtype=np.float64)
+        M.sort_indices()
+        self.n = M.shape[0]
+        self.indptr = np.ascontiguousarray(M.indptr, dtype=np.int64)
+        self.idx = np.ascontiguousarray(M.indices, dtype=np.int32)
+        self.w = None if np.all(M.data == 1.0) else np.ascontiguousarray(M.data, dtype=np.float64)
+        self.beta, self.J = float(beta), int(J)
+        self.L = katz_omp_lib()
+        self._scratch = {}
+
+    def __call__(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        shape = x.shape
+        x2 = np.ascontiguousarray(x.reshape(self.n, -1))
+        m = x2.shape[1]
+        if m not in self._scratch:
+            self._scratch[m] = (np.empty((self.n, m)), np.empty((self.n, m)))
+        t1, t2 = self._scratch[m]
+        y = np.empty((self.n, m))
+        wp = None if self.w is None else self.w.ctypes.data
+        self.L.katz_apply_omp(self.n, self.indptr, self.idx, wp, self.beta, self.J, m, x2, y, t1, t2)
+        return y.reshape(shape)
+
+
+def hope_sparse(A, d, beta, katz_tol=1e-12, terms=None, tol=0, maxiter=None, rng=0, ncv=None, threads=False):
+    # threads: False = scipy.sparse products on one core; True = oracle/katz_omp.c on the OpenMP default; int = that many
+    """threads=True: the Katz operator runs in oracle/katz_omp.c on all host cores (same arithmetic; for the
+    million-node reference arm of bench.py) instead of scipy.sparse products on one."""
     A = sp.csr_matrix(A, dtype=np.float64)
     AT = A.T.tocsr()
     n = A.shape[0]
     J = terms if terms is not None else katz_terms_needed(A, beta, katz_tol)
     counter = {'spmv': 0}
+    if threads:
+        if threads is not True:
+            katz_omp_lib().katz_omp_set_threads(int(threads))
+        kA, kAT = KatzOMP(A, beta, J), KatzOMP(AT, beta, J)
 
     def mv(x):
         counter['spmv'] += J
-        return katz_apply(A, beta, x, J)
+        return kA(x) if threads else katz_apply(A, beta, x, J)
 
     def rmv(x):
         counter['spmv'] += J
-        return katz_apply(AT, beta, x, J)
+        return kAT(x) if threads else katz_apply(AT, beta, x, J)
 
     S = spla.LinearOperator((n, n), matvec=mv, rmatvec=rmv, matmat=mv, rmatmat=rmv, dtype=np.float64)
     v0 = np.random.default_rng(rng).standard_normal(n)

@@ -25,11 +25,18 @@ def test_exports_match_header(native_lib):
     assert native_lib.gemb_version() == 100
 
 
-def test_struct_sizes_are_stable(native_lib):
+def test_struct_sizes_are_stable(native_lib, tmp_path):
+    """ctypes mirrors == the C structs of include/gemb200.h (compiled here with gcc), field by field in size."""
+    import subprocess
     from gem_b200 import _native
-    assert ctypes.sizeof(_native.HopeOpts) == 56
-    assert ctypes.sizeof(_native.HopeStats) == 104
-    assert ctypes.sizeof(_native.N2VStats) == 120
+    src = tmp_path / 'sz.c'
+    src.write_text('#include <stdio.h>\n#include "gemb200.h"\nint main(void){printf("%zu %zu %zu\\n", '
+                   'sizeof(gemb_hope_opts), sizeof(gemb_hope_stats), sizeof(gemb_n2v_stats));return 0;}\n')
+    exe = tmp_path / 'sz'
+    subprocess.check_call(['gcc', '-I', os.path.join(REPO, 'include'), str(src), '-o', str(exe)])
+    c_sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert [ctypes.sizeof(_native.HopeOpts), ctypes.sizeof(_native.HopeStats), ctypes.sizeof(_native.N2VStats)] == c_sizes
+    assert c_sizes == [72, 136, 120]         # an ABI change must be deliberate
 
 
 def test_no_cpu_fallback(native_lib):

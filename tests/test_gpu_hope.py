@@ -187,3 +187,48 @@ def test_power_law_graph_skewed_spectrum(gpu_ctx, hope_oracle, algorithm):
     rec = X[:, :k].astype(np.float64) @ X[:, k:].astype(np.float64).T
     reco = Xo[:, :k] @ Xo[:, k:].T
     assert np.linalg.norm(rec - reco) <= 5e-3 * np.linalg.norm(reco)      # fp32 vectors of the small-sigma end
+
+
+def test_bench_solver_setting_against_fp64_oracle(gpu_ctx, hope_oracle):
+    """the solver setting bench.py TIMES (bench.HOPE_SOLVER) compared with the fp64 oracle at a size
+    the oracle finishes (SBM n = 100k, same generator / density / d / beta as BASELINE configs[1]).  Tolerances are the
+    ones DESIGN.md section 6 states for the headline: the spectrum is one isolated value + a cluster of ~99 values within
+    a few percent, and k = 64 cuts inside the cluster, so individual cluster vectors are not comparable -- what is:
+      sigma        every one of the k values within 2e-3 relative of scipy svds(tol=1e-8) (top value 1e-5),
+      top-1 angle  the isolated top pair within 0.05 degrees of the oracle's,
+      residuals    max_j ||S v_j - sigma_j u_j||, ||S^T u_j - sigma_j v_j|| <= 1e-2 sigma_max against the fp64 operator
+                   (the oracle itself run at ARPACK tol=1e-3, the CPU arm's setting, is measured beside it),
+      orthonormal  |U^T U - I|, |V^T V - I| <= 1e-4."""
+    import os
+    import sys
+    from gem_b200 import synth
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    ho = hope_oracle
+    csr = synth.sbm(n=100_000, block=1000, seed=42)
+    d, beta = 128, 0.01
+    k = d // 2
+    m = _fresh_hope(d=d, beta=beta, compute_residual=1, **bench.HOPE_SOLVER)
+    X = m.learn_embedding(graph=csr)
+    sig = np.asarray(m._sigma, dtype=np.float64)
+    A = csr.to_scipy()
+    nthreads = min(32, os.cpu_count() or 1)
+    Xo, so, _ = ho.hope_sparse(A, d, beta, katz_tol=1e-12, tol=1e-8, threads=nthreads)
+    J = ho.katz_terms_needed(A, beta, 1e-12)
+    r1, r2, U, V = ho.svd_residuals(A, beta, X, J, sigma=sig)
+    ang = ho.principal_angles_deg(X[:, k - 1:k], Xo[:, k - 1:k])[0]
+    orth = max(np.abs(U.T @ U - np.eye(k)).max(), np.abs(V.T @ V - np.eye(k)).max())
+    # the CPU arm's own accuracy at its bench setting (ARPACK tol = 1e-3), for the record in the test log
+    Xc, sc, _ = ho.hope_sparse(A, d, beta, katz_tol=1e-7, tol=bench.HOPE_SOLVER['tol'], threads=nthreads)
+    c1, c2, _, _ = ho.svd_residuals(A, beta, Xc, J, sigma=sc)
+    print('bench-setting parity: sigma rel err max %.3g (top %.3g), top-1 angle %.3g deg, residual %.3g (GPU reports %.3g), '
+          'orth %.3g, iters %d, converged %d | scipy svds(tol=%g): sigma rel err %.3g, residual %.3g'
+          % (np.abs(sig / so - 1).max(), abs(sig[-1] / so[-1] - 1), ang, max(r1.max(), r2.max()), m.stats['resid_max'], orth,
+             m.stats['iters'], m.stats['converged'], bench.HOPE_SOLVER['tol'], np.abs(sc / so - 1).max(), max(c1.max(), c2.max())))
+    assert np.all(np.diff(sig) >= 0)
+    assert np.allclose(sig, so, rtol=2e-3), np.abs(sig / so - 1).max()
+    assert abs(sig[-1] / so[-1] - 1) < 1e-5
+    assert ang < 0.05
+    assert max(r1.max(), r2.max()) < 1e-2
+    assert orth < 1e-4
+    assert abs(m.stats['resid_max'] - max(r2.max(), 0)) < 2e-3          # the library's own fp32 residual tells the truth
