@@ -552,6 +552,7 @@ static int orth_rotated(HopeWork &W, const float *F, float *tmp, float *dst) {
 
 // ------------------------------------------------------------------------------------ symmetric solver
 static inline double katz_f(double beta, double l) { return beta * l / (1.0 - beta * l); }
+constexpr int GEMB_SWITCH_TO_LANCZOS = 1000;   // internal status of hope_symmetric (algorithm = 0 on a skewed spectrum)
 
 // nrm: tight estimate of ||A||_2 (power iteration), or < 0 when A is symmetric with non-negative weights: then
 // lambda_max = rho(A) >= |lambda_min| (Perron-Frobenius), so 1.05 * (largest Ritz value) bounds the spectrum on
@@ -643,6 +644,12 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         }
         R.change = change;
         th_prev = th_sorted;
+        // algorithm = 0 (auto): a first Rayleigh-Ritz round whose wanted values already span more than 3x -- a
+        // power-law spectrum -- is a case for restarted Lanczos: a filter that damps everything below the k-th value
+        // spreads the wanted columns over g^m and degenerates to power steps
+        if (it == 1 && o.algorithm == 0 && W.g->n >= 2048 && gval[order[k - 1]] < 0.33 * gval[order[0]] &&
+            gval[order[std::min(b - 1, 3)]] < 0.7 * gval[order[0]])
+            return GEMB_SWITCH_TO_LANCZOS;
         double stop_measure = change;
         if (o.stop_rule == 1) {
             // residual of the Ritz pairs from the Rayleigh-Ritz products alone: with V orthonormal and (l, z) an
@@ -790,6 +797,287 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
     return GEMB_OK;
 }
 
+// ------------------------------------------------------------------------------------ Lanczos solver
+// dst[:, col0 .. col0+w) (leading dimension ldd) = src (n x w, contiguous)
+__global__ void put_cols_kernel(int64_t n, int w, const float *__restrict__ src, float *__restrict__ dst, int ldd, int col0) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * w; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / w;
+        const int cc = (int)(i - r * w);
+        dst[r * ldd + col0 + cc] = src[i];
+    }
+}
+// dst[:, col_last - q] = src[:, q], q < w   (ascending-sigma column order of the result)
+__global__ void reverse_put_kernel(int64_t n, int w, const float *__restrict__ src, int lds, float *__restrict__ dst, int ldd, int col_last) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * w; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / w;
+        const int q = (int)(i - r * w);
+        dst[r * ldd + col_last - q] = src[r * lds + q];
+    }
+}
+__global__ void f64_to_f32_kernel(int count, const double *__restrict__ a, float *__restrict__ o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) o[i] = (float)a[i];
+}
+// Y (+)= a * X over count floats
+__global__ void axpy_kernel(int64_t count, float a, const float *__restrict__ X, float *__restrict__ Y, int accumulate) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        Y[i] = accumulate ? fmaf(a, X[i], Y[i]) : a * X[i];
+}
+
+// Thick-restart block Lanczos (block Krylov-Schur) on the symmetric A; S = f(A) shares its eigenvectors, so the
+// singular triplets of S are (|f(l)|, sign(f(l)) v, v) for the k eigenpairs with the largest |f(l)|.  This is the
+// block form of what ARPACK does behind scipy's svds (hope.py:33, SURVEY Appendix B: restarted Lanczos, ncv = 2k+1),
+// and it is the solver for power-law spectra (R-MAT, BASELINE configs[3]) on which Chebyshev-filtered subspace
+// iteration degenerates to power steps.
+//   basis Q (n x m, m <= m_max) in chunks of 64 columns; block width p = 16
+//   step:   W = A q_j (SpMM, width 16: the 64-byte rows of the input block stay L2-resident)
+//           H = Q^T W, W -= Q H, twice (classical Gram-Schmidt x 2; Gram and update on the tensor cores, b x b
+//           all-reduce on N GPUs); T[:, j] = H (T = Q^T A Q is kept explicitly, so the arrowhead left by a restart needs
+//           no special case); q_{j+1} R = W by CholeskyQR2
+//   full:   (theta, Y) = eigh(T); residual of Ritz pair i = || R Y[last block, i] || (no extra sweep);
+//           stop when |f'(theta_i)| res_i <= tol * sigma_max for the k wanted pairs;
+//           else keep the k + 16 best by |f|: Q <- Q Y_keep, T <- diag(theta_keep), continue with q_{j+1}
+static int hope_lanczos(HopeWork &W, const Opts &o, int d, float beta, double hard_bound, HopeResult &R) {
+    gemb_ctx *c = W.c;
+    const int k = d / 2, p = 16, cw = 64;
+    const int64_t rows = W.rows, shard = W.shard;
+    R.algorithm = 3;
+    R.katz_terms = 0;
+    const int k_keep = (k + p + p - 1) / p * p;
+    int m_max = o.lanczos_basis > 0 ? o.lanczos_basis : std::max(2 * k_keep, 160);
+    m_max = (m_max + p - 1) / p * p;
+    GEMB_ARG(m_max >= k_keep + 2 * p && m_max <= 1024, "algorithm3_basis");
+    const int nchunk = (m_max + cw - 1) / cw;
+    const int mt = m_max + p;                                    // T carries the coupling block of the next q too
+    const size_t chunk_bytes = sizeof(float) * (size_t)shard * cw;
+    std::vector<float *> Q(nchunk, nullptr), Qn((k_keep + cw - 1) / cw, nullptr);
+    struct Free { std::vector<float *> *a, *b; float *t[3]; double *g[3]; float *m32;
+                  ~Free() { for (auto x : *a) dfree(x); for (auto x : *b) dfree(x); for (auto x : t) dfree(x); for (auto x : g) dfree(x); dfree(m32); } }
+        guard{&Q, &Qn, {nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}, nullptr};
+    for (auto &q : Q) { GEMB_CUDA(dmalloc(&q, chunk_bytes ? chunk_bytes : 4)); GEMB_CUDA(cudaMemsetAsync(q, 0, chunk_bytes, c->stream)); }
+    for (auto &q : Qn) { GEMB_CUDA(dmalloc(&q, chunk_bytes ? chunk_bytes : 4)); }
+    // narrow blocks: Vcur (SpMM input: a halo block on N GPUs), Wb, Tb
+    float *Vcur = W.buf[0], *Wb = W.buf[1], *Tb = W.buf[2], *Tmp64 = nullptr;
+    GEMB_CUDA(dmalloc(&guard.t[0], chunk_bytes ? chunk_bytes : 4));
+    Tmp64 = guard.t[0];
+    double *Gd = nullptr, *Td = nullptr, *Yd = nullptr;          // device: small Gram (cw x p), T (m x m), Y
+    GEMB_CUDA(dmalloc(&guard.g[0], sizeof(double) * (size_t)cw * cw)); Gd = guard.g[0];
+    GEMB_CUDA(dmalloc(&guard.g[1], sizeof(double) * (size_t)mt * mt)); Td = guard.g[1];
+    GEMB_CUDA(dmalloc(&guard.g[2], sizeof(double) * (size_t)mt * mt)); Yd = guard.g[2];
+    GEMB_CUDA(dmalloc(&guard.m32, sizeof(float) * (size_t)cw * cw));
+    float *M32 = guard.m32;
+    double *wd = nullptr, *Zs = nullptr;
+    GEMB_CUDA(dmalloc(&wd, sizeof(double) * mt));
+    GEMB_CUDA(dmalloc(&Zs, sizeof(double) * (size_t)mt * mt));
+    struct Free2 { double *a, *b; ~Free2() { dfree(a); dfree(b); } } guard2{wd, Zs};
+
+    const int grid_el = c->sm_count * 8;
+    auto gram_ar = [&](const float *P, int b1, const float *Qp, int b2, double *G) -> int {
+        GEMB_TRY(c->t_dense.begin(c->stream));
+        GEMB_TRY(gram_launch(c, rows, P, b1, Qp, b2, G));
+        GEMB_TRY(c->t_dense.end(c->stream));
+        return comm_allreduce_f64(W, G, (size_t)b1 * b2);
+    };
+    // CholeskyQR2 of the n x p block `src` in place (scratch Tb); Rout (p x p, host, row-major upper) = R2 * R1
+    std::vector<double> Rh((size_t)p * p), R1((size_t)p * p), R2((size_t)p * p), Ginv((size_t)p * p);
+    auto cholqr_p = [&](float *src, float *scratch, double *Rout) -> int {
+        for (int pass = 0; pass < 2; pass++) {
+            GEMB_TRY(gram_ar(src, p, src, p, W.G));
+            GEMB_TRY(c->t_dense.begin(c->stream));
+            GEMB_TRY(chol_inverse_launch(c, p, W.G, W.Minv, W.rank_dev, W.G2));     // G2 = R^-1 (fp64)
+            GEMB_TRY(apply_launch(c, rows, src, p, W.Minv, p, p, scratch, p));
+            GEMB_TRY(c->t_dense.end(c->stream));
+            GEMB_CUDA(cudaMemcpyAsync(src, scratch, sizeof(float) * (size_t)rows * p, cudaMemcpyDeviceToDevice, c->stream));
+            GEMB_CUDA(cudaMemcpyAsync(Ginv.data(), W.G2, sizeof(double) * p * p, cudaMemcpyDeviceToHost, c->stream));
+            GEMB_CUDA(cudaStreamSynchronize(c->stream));
+            // invert the upper-triangular R^-1 on the host (p = 16): R = (R^-1)^-1; dropped columns (zero pivot) stay zero
+            std::vector<double> &Rt = pass == 0 ? R1 : R2;
+            std::fill(Rt.begin(), Rt.end(), 0.0);
+            for (int j = 0; j < p; j++) {
+                if (Ginv[(size_t)j * p + j] == 0.0) continue;
+                Rt[(size_t)j * p + j] = 1.0 / Ginv[(size_t)j * p + j];
+                for (int i = j - 1; i >= 0; i--) {
+                    if (Ginv[(size_t)i * p + i] == 0.0) continue;
+                    double sacc = 0.0;
+                    for (int l = i + 1; l <= j; l++) sacc += Ginv[(size_t)i * p + l] * Rt[(size_t)l * p + j];
+                    Rt[(size_t)i * p + j] = -sacc / Ginv[(size_t)i * p + i];
+                }
+            }
+        }
+        for (int i = 0; i < p; i++)
+            for (int j = 0; j < p; j++) {
+                double a = 0.0;
+                for (int l = 0; l < p; l++) a += R2[(size_t)i * p + l] * R1[(size_t)l * p + j];
+                Rout[(size_t)i * p + j] = a;
+            }
+        return GEMB_OK;
+    };
+
+    std::vector<double> T((size_t)mt * mt, 0.0), Hcol((size_t)m_max * p), Hc((size_t)cw * p), theta(m_max), Y((size_t)m_max * m_max);
+    std::vector<double> fabsv(m_max);
+    std::vector<int> order(m_max);
+    GEMB_TRY(randn_launch(c, rows, p, o.seed, (uint64_t)W.g->row0, Vcur));
+    GEMB_TRY(cholqr_p(Vcur, Tb, Rh.data()));
+    int m = 0, restarts = 0, steps = 0;
+    double bound = hard_bound * 1.02 + 1e-30;
+    const int max_steps = std::max(o.max_iters, 1) * (m_max / p);
+    bool done = false;
+    while (!done) {
+        // ---- append q_j, expand
+        put_cols_kernel<<<grid_el, 256, 0, c->stream>>>(rows, p, Vcur, Q[m / cw], cw, m % cw);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+        const int j0 = m;
+        m += p;
+        steps++;
+        GEMB_TRY(publish(W, Vcur, p));
+        GEMB_TRY(dist_spmm3(W, false, p, 1.f, Vcur, 0.f, false, 1.f, nullptr, Wb, true, false));
+        std::fill(Hcol.begin(), Hcol.end(), 0.0);
+        const int nc_live = (m + cw - 1) / cw;
+        for (int pass = 0; pass < 2; pass++) {
+            for (int cc = 0; cc < nc_live; cc++) {
+                GEMB_TRY(gram_ar(Q[cc], cw, Wb, p, Gd));                               // H_c = Q_c^T W   (cw x p)
+                GEMB_TRY(c->t_dense.begin(c->stream));
+                f64_to_f32_kernel<<<(cw * p + 255) / 256, 256, 0, c->stream>>>(cw * p, Gd, M32);
+                GEMB_CUDA(cudaGetLastError());
+                GEMB_TRY(apply_launch(c, rows, Q[cc], cw, M32, p, p, Tb, p));           // Q_c H_c
+                axpy_kernel<<<grid_el, 256, 0, c->stream>>>(rows * (int64_t)p, -1.f, Tb, Wb, 1);
+                GEMB_CUDA(cudaGetLastError());
+                count_launch(2);
+                GEMB_TRY(c->t_dense.end(c->stream));
+                GEMB_CUDA(cudaMemcpyAsync(Hc.data(), Gd, sizeof(double) * cw * p, cudaMemcpyDeviceToHost, c->stream));
+                GEMB_CUDA(cudaStreamSynchronize(c->stream));
+                for (int r = 0; r < cw && cc * cw + r < m; r++)
+                    for (int q = 0; q < p; q++) Hcol[(size_t)(cc * cw + r) * p + q] += Hc[(size_t)r * p + q];
+            }
+        }
+        for (int r = 0; r < m; r++)
+            for (int q = 0; q < p; q++) {
+                const double v = Hcol[(size_t)r * p + q];
+                T[(size_t)r * mt + j0 + q] = v;
+                T[(size_t)(j0 + q) * mt + r] = v;
+            }
+        for (int a2 = 0; a2 < p; a2++)                                                   // symmetrise the diagonal block
+            for (int b2 = a2 + 1; b2 < p; b2++) {
+                const double v = 0.5 * (T[(size_t)(j0 + a2) * mt + j0 + b2] + T[(size_t)(j0 + b2) * mt + j0 + a2]);
+                T[(size_t)(j0 + a2) * mt + j0 + b2] = v;
+                T[(size_t)(j0 + b2) * mt + j0 + a2] = v;
+            }
+        GEMB_TRY(cholqr_p(Wb, Tb, Rh.data()));                                           // q_{j+1} R = W
+        // Vcur = q_{j+1}: always work block 0 (on N GPUs its halo is the one the peers fill), a 64-byte-per-row copy
+        GEMB_CUDA(cudaMemcpyAsync(Vcur, Wb, sizeof(float) * (size_t)rows * p, cudaMemcpyDeviceToDevice, c->stream));
+        const bool full = m + p > m_max;
+        if (!full && steps < max_steps) continue;
+
+        // ---- Rayleigh-Ritz on T[0:m, 0:m]
+        std::vector<double> Tm((size_t)m * m);
+        for (int r = 0; r < m; r++) for (int q = 0; q < m; q++) Tm[(size_t)r * m + q] = T[(size_t)r * mt + q];
+        GEMB_CUDA(cudaMemcpyAsync(Td, Tm.data(), sizeof(double) * m * m, cudaMemcpyHostToDevice, c->stream));
+        GEMB_TRY(c->t_dense.begin(c->stream));
+        GEMB_TRY(eigh_launch(c, m, Td, wd, Yd, Zs, 1e-12));
+        GEMB_TRY(c->t_dense.end(c->stream));
+        GEMB_CUDA(cudaMemcpyAsync(theta.data(), wd, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaMemcpyAsync(Y.data(), Yd, sizeof(double) * m * m, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        double amax = 0.0;
+        for (int i = 0; i < m; i++) amax = std::max(amax, fabs(theta[i]));
+        bound = std::min(hard_bound * 1.02, 1.02 * amax) + 1e-30;
+        for (int i = 0; i < m; i++) fabsv[i] = fabs(katz_f(beta, std::max(-bound, std::min(bound, theta[i]))));
+        std::iota(order.begin(), order.begin() + m, 0);
+        std::sort(order.begin(), order.begin() + m, [&](int a2, int b2) { return fabsv[a2] > fabsv[b2]; });
+        const double smax = std::max(fabsv[order[0]], 1e-300);
+        double worst = 0.0;
+        for (int jj = 0; jj < std::min(k, m); jj++) {
+            const int col = order[jj];
+            double r2 = 0.0;
+            for (int a2 = 0; a2 < p; a2++) {
+                double t = 0.0;
+                for (int b2 = 0; b2 < p; b2++) t += Rh[(size_t)a2 * p + b2] * Y[(size_t)(m - p + b2) * m + col];
+                r2 += t * t;
+            }
+            const double l = std::max(-bound, std::min(bound, theta[col]));
+            const double fp = (double)beta / ((1.0 - beta * l) * (1.0 - beta * l));
+            worst = std::max(worst, fp * sqrt(r2) / smax);
+        }
+        R.change = worst;
+        R.resid_est = (float)worst;
+        restarts++;
+        R.iters = restarts;
+        if (o.verbose)
+            fprintf(stderr, "[gemb_hope/lanczos] restart %d  basis %d  steps %d  sigma_max %.6g sigma_k %.6g  residual %.3g\n", restarts, m,
+                    steps, smax, fabsv[order[std::min(k, m) - 1]], worst);
+        const bool conv = m >= k && worst <= (double)o.tol;
+        if (conv) R.converged = 1;
+        done = conv || steps >= max_steps;
+        // ---- compress: Q <- Q Y[:, keep]   (keep = the k_keep best by |f|; on exit: the k wanted, scaled for X)
+        const int nk = done ? k : std::min(k_keep, m);
+        const int ncn = (nk + cw - 1) / cw;
+        for (int oc = 0; oc < ncn; oc++) {
+            const int ow = std::min(cw, nk - oc * cw);
+            for (int cc = 0; cc < nc_live; cc++) {
+                std::vector<float> Mh((size_t)cw * cw, 0.f);
+                for (int r = 0; r < cw && cc * cw + r < m; r++)
+                    for (int q = 0; q < ow; q++) Mh[(size_t)r * cw + q] = (float)Y[(size_t)(cc * cw + r) * m + order[oc * cw + q]];
+                GEMB_CUDA(cudaMemcpyAsync(M32, Mh.data(), sizeof(float) * cw * cw, cudaMemcpyHostToDevice, c->stream));
+                GEMB_CUDA(cudaStreamSynchronize(c->stream));
+                GEMB_TRY(c->t_dense.begin(c->stream));
+                GEMB_TRY(apply_launch(c, rows, Q[cc], cw, M32, cw, cw, cc == 0 ? Qn[oc] : Tmp64, cw));
+                if (cc > 0) {
+                    axpy_kernel<<<grid_el, 256, 0, c->stream>>>(rows * (int64_t)cw, 1.f, Tmp64, Qn[oc], 1);
+                    GEMB_CUDA(cudaGetLastError());
+                    count_launch();
+                }
+                GEMB_TRY(c->t_dense.end(c->stream));
+            }
+        }
+        if (done) {
+            // X = [ v sign(f) sqrt(sigma) | v sqrt(sigma) ], sigma ascending
+            std::vector<float> sig(k);
+            R.sigma_max = smax;
+            R.Xd = nullptr;
+            GEMB_CUDA(dmalloc(&R.Xalloc, sizeof(float) * (size_t)std::max<int64_t>(rows, 1) * d));
+            R.Xd = R.Xalloc;
+            GEMB_ARG(k <= cw * (int)Qn.size(), "k");
+            // per-column scaling on the host: column jj of Qn <-> order[jj] (descending |f|); output column k-1-jj
+            std::vector<float> Ms((size_t)cw * cw), Mt((size_t)cw * cw);
+            for (int oc = 0; oc < ncn; oc++) {
+                const int ow = std::min(cw, k - oc * cw);
+                std::fill(Ms.begin(), Ms.end(), 0.f); std::fill(Mt.begin(), Mt.end(), 0.f);
+                for (int q = 0; q < ow; q++) {
+                    const int jj = oc * cw + q, col = order[jj];
+                    const double l = std::max(-bound, std::min(bound, theta[col]));
+                    const double f = katz_f(beta, l), sg = fabs(f), rt = sqrt(sg);
+                    sig[k - 1 - jj] = (float)sg;
+                    Ms[(size_t)q * cw + q] = (float)(f < 0 ? -rt : rt);
+                    Mt[(size_t)q * cw + q] = (float)rt;
+                }
+                for (int half = 0; half < 2; half++) {
+                    GEMB_CUDA(cudaMemcpyAsync(M32, (half == 0 ? Ms : Mt).data(), sizeof(float) * cw * cw, cudaMemcpyHostToDevice, c->stream));
+                    GEMB_CUDA(cudaStreamSynchronize(c->stream));
+                    GEMB_TRY(apply_launch(c, rows, Qn[oc], cw, M32, cw, cw, Tmp64, cw));
+                    // reversed column order into X: source column q -> X column (half*k) + k-1-(oc*cw+q)
+                    reverse_put_kernel<<<grid_el, 256, 0, c->stream>>>(rows, ow, Tmp64, cw, R.Xd, d, half * k + k - 1 - oc * cw);
+                    GEMB_CUDA(cudaGetLastError());
+                    count_launch();
+                }
+            }
+            R.sig_dev = (float *)W.G2;
+            GEMB_CUDA(cudaMemcpyAsync(R.sig_dev, sig.data(), sizeof(float) * k, cudaMemcpyHostToDevice, c->stream));
+            GEMB_CUDA(cudaStreamSynchronize(c->stream));
+            break;
+        }
+        // ---- restart: new basis = Qn (nk columns), T = diag(theta_keep); q_{j+1} (= Vcur) is appended next
+        for (int oc = 0; oc < nchunk; oc++) {
+            if (oc < ncn) GEMB_CUDA(cudaMemcpyAsync(Q[oc], Qn[oc], chunk_bytes, cudaMemcpyDeviceToDevice, c->stream));
+            else GEMB_CUDA(cudaMemsetAsync(Q[oc], 0, chunk_bytes, c->stream));
+        }
+        std::fill(T.begin(), T.end(), 0.0);
+        for (int q = 0; q < nk; q++) T[(size_t)q * mt + q] = theta[order[q]];
+        m = nk;
+    }
+    return GEMB_OK;
+}
+
 // ---- 'SVD error (low rank)' of hope.py:38-40
 __global__ void split_halves_kernel(int64_t n, int d, const float *__restrict__ X, float *__restrict__ L, float *__restrict__ Rr) {
     const int k = d / 2;
@@ -812,10 +1100,6 @@ __global__ void probe_block_kernel(int64_t n, int w, int64_t p0, int probe, uint
         } else v = (r == p0 + cc) ? 1.f : 0.f;
         Z[i] = v;
     }
-}
-__global__ void f64_to_f32_kernel(int count, const double *__restrict__ a, float *__restrict__ o) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) o[i] = (float)a[i];
 }
 
 }  // namespace gemb
@@ -981,7 +1265,7 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     double nrm = 0.0, hard_bound = 0.0;
     int J = o.katz_terms;
     bool need_power = (J <= 0 && algo == 1);
-    if (algo == 2) {
+    if (algo >= 2) {
         bool nonneg = false;
         GEMB_TRY(rowsum_bound(W, &hard_bound, &nonneg));
         if (nonneg && (double)beta * hard_bound * 1.02 < 1.0) nrm = -1.0;   // spectrum bounds from Ritz values
@@ -1012,7 +1296,14 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
     }
 
     HopeResult R;
-    int s = (algo == 2) ? hope_symmetric(W, o, d, beta, nrm, hard_bound, R) : hope_general(W, o, d, beta, J, R);
+    int s;
+    // thick-restart Lanczos needs room for its basis (k + 16 kept + expansions); tiny graphs take the subspace solver
+    const bool lanczos_fits = g->n >= 2048;
+    if (algo == 3 && lanczos_fits) s = hope_lanczos(W, o, d, beta, hard_bound > 0 ? hard_bound : nrm, R);
+    else if (algo >= 2) {
+        s = hope_symmetric(W, o, d, beta, nrm, hard_bound, R);
+        if (s == GEMB_SWITCH_TO_LANCZOS) { R = HopeResult(); s = hope_lanczos(W, o, d, beta, hard_bound > 0 ? hard_bound : nrm, R); }
+    } else s = hope_general(W, o, d, beta, J, R);
     if (s != GEMB_OK) { dfree(R.Xalloc); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return s; }
 
     GEMB_CUDA(cudaEventRecord(ev1, c->stream));

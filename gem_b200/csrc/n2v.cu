@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <numeric>
 #include <chrono>
+#include <cub/cub.cuh>
 
 namespace gemb {
 
@@ -115,6 +116,112 @@ __global__ void walk_kernel(const int32_t *__restrict__ indptr, const int32_t *_
         }
     }
     for (; len < walk_len; len++) row[len] = 0;   // WalksVV is zero-initialised
+}
+
+// ------------------------------------------------------------------------------ second-order tables (p, q != 1)
+// PreprocessNode (bin@0x411f40): every directed edge (t -> v) owns an alias table over v's out-neighbours x with the
+// unnormalised weights  w(v,x)/p if x == t;  w(v,x) if x is an out-neighbour of t;  w(v,x)/q otherwise  -- the
+// sum over edges of outdeg(v) entries the reference keeps in a hash map per node.  Here: one flat array, the table
+// of CSR edge e at off2[e], built by one thread per edge with the oracle's exact fp64 operation order (sequential sum,
+// division by the sum, Vose with LIFO stacks), adjacency membership by binary search in t's sorted neighbour list.
+__global__ void edge_degree_kernel(int64_t nnz, const int32_t *__restrict__ indptr, const int32_t *__restrict__ idx,
+                                   long long *__restrict__ deg_out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        const int v = idx[e];
+        deg_out[e] = (long long)(indptr[v + 1] - indptr[v]);
+    }
+}
+
+__device__ __forceinline__ bool has_edge_sorted(const int32_t *__restrict__ idx, int lo, int hi, int x) {
+    const int end = hi;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (idx[m] < x) lo = m + 1; else hi = m; }
+    return lo < end && idx[lo] == x;
+}
+
+__global__ void alias2_build_kernel(int64_t n, int64_t nnz, const int32_t *__restrict__ indptr, const int32_t *__restrict__ idx,
+                                    const double *__restrict__ w, const long long *__restrict__ off2, double p, double q,
+                                    int32_t *__restrict__ K2, double *__restrict__ U2, int32_t *__restrict__ scratch) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    // source node t of CSR position e: last row with indptr[row] <= e
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if ((int64_t)indptr[m + 1] <= e) lo = m + 1; else hi = m; }
+    const int t = (int)lo;
+    const int v = idx[e];
+    const int s = indptr[v], d = indptr[v + 1] - s;
+    if (d == 0) return;
+    const int ts = indptr[t], te = indptr[t + 1];
+    const long long o = off2[e];
+    int32_t *K = K2 + o, *st = scratch + o;
+    double *U = U2 + o;
+    double psum = 0.0;
+    for (int j = 0; j < d; j++) {
+        const int x = idx[s + j];
+        const double wj = w ? w[s + j] : 1.0;
+        double val;
+        if (x == t) val = __ddiv_rn(wj, p);
+        else if (has_edge_sorted(idx, ts, te, x)) val = wj;
+        else val = __ddiv_rn(wj, q);
+        U[j] = val;
+        psum = __dadd_rn(psum, val);
+    }
+    int nu = 0, no = 0;
+    for (int i = 0; i < d; i++) {
+        const double u = __dmul_rn(__ddiv_rn(U[i], psum), (double)d);
+        K[i] = 0;
+        U[i] = u;
+        if (u < 1.0) st[nu++] = i; else st[d - 1 - (no++)] = i;
+    }
+    while (nu > 0 && no > 0) {
+        const int small = st[--nu];
+        const int large = st[d - 1 - (--no)];
+        K[small] = large;
+        const double ul = __dadd_rn(__dadd_rn(U[large], U[small]), -1.0);
+        U[large] = ul;
+        if (ul < 1.0) st[nu++] = large; else st[d - 1 - (no++)] = large;
+    }
+    while (nu > 0) U[st[--nu]] = 1.0;
+    while (no > 0) U[st[d - 1 - (--no)]] = 1.0;
+}
+
+// SimulateWalk with the table of the edge just walked (bin@0x411d73); same stream offsets as walk_kernel
+__global__ void walk2_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ idx,
+                             const int32_t *__restrict__ K2, const double *__restrict__ U2,
+                             const long long *__restrict__ off2, const int32_t *__restrict__ order, int64_t N,
+                             int walk_len, uint32_t seed, int64_t w_begin, int64_t w_end, int32_t *__restrict__ out) {
+    const int64_t w = w_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= w_end) return;
+    int32_t *row = out + (w - w_begin) * walk_len;
+    const int64_t i = w / N;
+    const uint64_t per_walk = walk_len >= 2 ? (uint64_t)(2 * walk_len - 3) : 0;
+    uint32_t st = lcg_skip(seed, (uint64_t)(i + 1) * (uint64_t)(N - 1) + (uint64_t)w * per_walk);
+    int cur = order[w];
+    int len = 0;
+    row[len++] = cur;
+    if (walk_len > 1) {
+        int s = indptr[cur], d = indptr[cur + 1] - s;
+        if (d > 0) {
+            st = lcg_next(st);
+            int64_t e = s + (int)(st % (uint32_t)d);         // step 1: uniform, ignores weights (bin@0x411b31)
+            cur = idx[e];
+            row[len++] = cur;
+            while (len < walk_len) {
+                s = indptr[cur];
+                d = indptr[cur + 1] - s;
+                if (d == 0) break;
+                const long long o = off2[e];
+                st = lcg_next(st);
+                const int x = (int)(int64_t)__dmul_rn(lcg_uni(st), (double)d);
+                st = lcg_next(st);
+                const double y = lcg_uni(st);
+                const int nx = y < U2[o + x] ? x : K2[o + x];
+                e = s + nx;
+                cur = idx[e];
+                row[len++] = cur;
+            }
+        }
+    }
+    for (; len < walk_len; len++) row[len] = 0;
 }
 
 // ------------------------------------------------------------------------------ vocabulary
@@ -425,7 +532,13 @@ struct N2VDev {
     double *UT = nullptr;
     float *syn_pos = nullptr, *syn_neg = nullptr, *pos0 = nullptr, *delta = nullptr;
     uint32_t *seq_state = nullptr;
+    bool second_order = false;
+    long long *off2 = nullptr;       // nnz + 1: table offset of every CSR edge
+    int32_t *K2 = nullptr;
+    double *U2 = nullptr;
+    long long table_entries = 0;
     ~N2VDev() {
+        dfree(off2); dfree(K2); dfree(U2);
         dfree(w); dfree(U); dfree(K); dfree(scratch); dfree(order); dfree(walks);
         dfree(first_pos); dfree(cnt); dfree(pairs); dfree(KT); dfree(tok2node); dfree(UT); dfree(ent);
         dfree(syn_pos); dfree(syn_neg); dfree(pos0); dfree(delta); dfree(seq_state);
@@ -438,7 +551,10 @@ static int check_graph_for_n2v(gemb_graph *g) {
     return GEMB_OK;
 }
 
-static int build_alias(gemb_graph *g, const double *weights64, N2VDev &D) {
+static int build_alias2(gemb_graph *g, const double *weights64, double p, double q, N2VDev &D);
+
+static int build_alias(gemb_graph *g, const double *weights64, N2VDev &D, double p = 1.0, double q = 1.0) {
+    if (p != 1.0 || q != 1.0) return build_alias2(g, weights64, p, q, D);
     gemb_ctx *c = g->ctx;
     const int64_t nnz = g->A.nnz;
     GEMB_CUDA(dmalloc(&D.K, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
@@ -452,6 +568,58 @@ static int build_alias(gemb_graph *g, const double *weights64, N2VDev &D) {
     alias_build_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(n, g->A.indptr, D.w, D.K, D.U, D.scratch);
     GEMB_CUDA(cudaGetLastError());
     count_launch();
+    return GEMB_OK;
+}
+
+static int build_alias2(gemb_graph *g, const double *weights64, double p, double q, N2VDev &D) {
+    gemb_ctx *c = g->ctx;
+    const int64_t nnz = g->A.nnz, n = g->n;
+    D.second_order = true;
+    if (weights64 && nnz) {
+        GEMB_CUDA(dmalloc(&D.w, sizeof(double) * nnz));
+        GEMB_CUDA(cudaMemcpyAsync(D.w, weights64, sizeof(double) * nnz, cudaMemcpyHostToDevice, c->stream));
+    }
+    GEMB_CUDA(dmalloc(&D.off2, sizeof(long long) * (nnz + 1)));
+    long long *deg = nullptr;
+    GEMB_CUDA(dmalloc(&deg, sizeof(long long) * (nnz + 1)));
+    GEMB_CUDA(cudaMemsetAsync(deg, 0, sizeof(long long) * (nnz + 1), c->stream));
+    if (nnz) {
+        edge_degree_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(nnz, g->A.indptr, g->A.indices, deg);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, deg, D.off2, nnz + 1, c->stream);
+    void *tmp = nullptr;
+    GEMB_CUDA(dmalloc(&tmp, tb ? tb : 4));
+    GEMB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, deg, D.off2, nnz + 1, c->stream));
+    count_launch();
+    long long T = 0;
+    GEMB_CUDA(cudaMemcpyAsync(&T, D.off2 + nnz, sizeof T, cudaMemcpyDeviceToHost, c->stream));
+    GEMB_CUDA(cudaStreamSynchronize(c->stream));
+    dfree(deg); dfree(tmp);
+    D.table_entries = T;
+    // the reference needs the same sum_(t->v) outdeg(v) entries in host hash maps; here they must fit in HBM
+    size_t free_b = 0, total_b = 0;
+    GEMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double need = 16.0 * (double)T;
+    if (need > 0.9 * ((double)free_b + (double)gemb_mem_cached_bytes())) {
+        set_error("node2vec with p=%g q=%g: the second-order alias tables have %lld entries (%.1f GB, sum over edges (t->v) of "
+                  "outdeg(v)) and do not fit in the %.1f GB of free device memory", p, q, T, need / 1e9, (double)free_b / 1e9);
+        return GEMB_ERR_NOMEM;
+    }
+    GEMB_CUDA(dmalloc(&D.K2, sizeof(int32_t) * std::max<long long>(T, 1)));
+    GEMB_CUDA(dmalloc(&D.U2, sizeof(double) * std::max<long long>(T, 1)));
+    GEMB_CUDA(dmalloc(&D.scratch, sizeof(int32_t) * std::max<long long>(T, 1)));
+    if (nnz) {
+        alias2_build_kernel<<<(unsigned)((nnz + 127) / 128), 128, 0, c->stream>>>(n, nnz, g->A.indptr, g->A.indices, D.w, D.off2,
+                                                                                 p, q, D.K2, D.U2, D.scratch);
+        GEMB_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    GEMB_CUDA(cudaStreamSynchronize(c->stream));
+    dfree(D.scratch);
+    D.scratch = nullptr;
     return GEMB_OK;
 }
 
@@ -472,8 +640,12 @@ static int run_walks(gemb_graph *g, N2VDev &D, const int32_t *nids, int64_t N, i
     const int64_t cnt = w_end - w_begin;
     GEMB_CUDA(dmalloc(&D.walks, sizeof(int32_t) * std::max<int64_t>(cnt * walk_len, 1)));
     if (cnt > 0) {
-        walk_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, c->stream>>>(g->A.indptr, g->A.indices, D.K, D.U, D.order,
-                                                                         N, walk_len, seed, w_begin, w_end, D.walks);
+        if (D.second_order)
+            walk2_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, c->stream>>>(g->A.indptr, g->A.indices, D.K2, D.U2, D.off2, D.order,
+                                                                              N, walk_len, seed, w_begin, w_end, D.walks);
+        else
+            walk_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, c->stream>>>(g->A.indptr, g->A.indices, D.K, D.U, D.order,
+                                                                             N, walk_len, seed, w_begin, w_end, D.walks);
         GEMB_CUDA(cudaGetLastError());
     count_launch();
     }
@@ -534,10 +706,7 @@ static int n2v_check_common(int64_t N, int walk_len, int num_walks, double p, do
     GEMB_ARG(N >= 1, "N");
     GEMB_ARG(walk_len >= 1 && num_walks >= 1, "walk_len / num_walks");
     GEMB_ARG(seed >= 1 && seed < 2147483647, "seed must be in [1, 2^31-2] (TRnd)");
-    if (p != 1.0 || q != 1.0) {
-        set_error("node2vec on the GPU implements p = q = 1 (first-order alias tables); got p=%g q=%g", p, q);
-        return GEMB_ERR_UNSUPPORTED;
-    }
+    GEMB_ARG(p > 0.0 && q > 0.0, "p and q must be positive");
     return GEMB_OK;
 }
 
@@ -555,7 +724,7 @@ int gemb_n2v_walks(gemb_graph *g, const double *weights64, const int32_t *nids, 
     cudaEvent_t e0, e1, e2;
     GEMB_CUDA(cudaEventCreate(&e0)); GEMB_CUDA(cudaEventCreate(&e1)); GEMB_CUDA(cudaEventCreate(&e2));
     GEMB_CUDA(cudaEventRecord(e0, c->stream));
-    GEMB_TRY(build_alias(g, weights64, D));
+    GEMB_TRY(build_alias(g, weights64, D, p, q));
     GEMB_CUDA(cudaEventRecord(e1, c->stream));
     double sh_ms = 0;
     GEMB_TRY(run_walks(g, D, nids, N, walk_len, num_walks, (uint32_t)seed, w_begin, w_end, &sh_ms));
@@ -595,7 +764,7 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
     cudaEvent_t ev[6];
     for (auto &e : ev) GEMB_CUDA(cudaEventCreate(&e));
     GEMB_CUDA(cudaEventRecord(ev[0], c->stream));
-    GEMB_TRY(build_alias(g, weights64, D));
+    GEMB_TRY(build_alias(g, weights64, D, p, q));
     GEMB_CUDA(cudaEventRecord(ev[1], c->stream));
 
     // ---- walks: this rank's contiguous share of the num_walks*N walks of an epoch
@@ -607,6 +776,7 @@ int gemb_node2vec(gemb_graph *g, const double *weights64, const int32_t *nids, i
     double sh_ms = 0;
     GEMB_TRY(run_walks(g, D, nids, N, walk_len, num_walks, (uint32_t)seed, w_begin, w_end, &sh_ms));
     GEMB_CUDA(cudaEventRecord(ev[2], c->stream));
+    if (D.second_order) { dfree(D.K2); dfree(D.U2); dfree(D.off2); D.K2 = nullptr; D.U2 = nullptr; D.off2 = nullptr; }   // tables are walk-only
 
     // ---- vocabulary: first appearance + counts (all ranks combined), host renumbering + Vose
     auto tv0 = std::chrono::steady_clock::now();

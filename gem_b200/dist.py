@@ -36,3 +36,28 @@ def init_comm_from_torch(ctx, dist_module, rank, world):
     uid = [_native.comm_unique_id() if rank == 0 else None]
     dist_module.broadcast_object_list(uid, src=0)
     ctx.comm_init(rank, world, uid[0])
+
+
+def halo_plan(n, row0, n_shard, indices):
+    """Host-side statement of gem_b200/csrc/halo.cu::halo_build for one rank (NumPy; the library does the same on the
+    device with cub): H = the sorted distinct REMOTE columns the shard references; indices_ext = the column ids with
+    local columns renumbered to [0, n_shard) and remote ones to n_shard + (position in H)."""
+    indices = np.asarray(indices, dtype=np.int64)
+    lo, hi = row0, min(row0 + n_shard, n)
+    remote = (indices < lo) | (indices >= hi)
+    H = np.unique(indices[remote])
+    ext = np.where(remote, n_shard + np.searchsorted(H, indices), indices - lo)
+    return H.astype(np.int32), ext.astype(np.int32)
+
+
+def push_lists(H_all, row0, n_shard, n, rank):
+    """Who needs my rows: for every peer q the slots of H_q that fall into [row0, row0 + n_shard) -> (local row, q, slot)."""
+    lo, hi = row0, min(row0 + n_shard, n)
+    out = []
+    for q, H in enumerate(H_all):
+        if q == rank:
+            continue
+        a, b = np.searchsorted(H, lo), np.searchsorted(H, hi)
+        for slot in range(a, b):
+            out.append((int(H[slot]) - lo, q, slot))
+    return out

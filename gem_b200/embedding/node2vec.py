@@ -8,10 +8,16 @@ Same class name (lower case), hyper-parameters (d, max_iter, walk_len, num_walks
 inout_p), method name, signature, errors and row convention (row index = integer node id,
 graph_util.py:168; V rows where V-1 is the largest id, phantom row 0 if walks were padded: SURVEY F10).
 
+ret_p / inout_p = 1 use one alias table per node; any other positive values build the reference's second-order
+tables (one per directed edge (t -> v), sum_(t->v) outdeg(v) entries) on the device -- walks stay bit-exact against the
+CPU restatement of the binary; a graph whose tables do not fit in HBM fails with the size in the message.
+
 Extra optional hyper-parameters: seed (the binary uses time(NULL); default 1), device,
 sequential (parity mode: one warp follows the single-threaded binary's RNG stream), dtype.
 There is no CPU path: without a GPU learn_embedding raises RuntimeError.
 """
+import os
+
 import numpy as np
 
 from gem_b200 import _native
@@ -48,8 +54,18 @@ class node2vec(StaticGraphEmbedding):
             csr, nids = graph
         else:
             csr, nids = _graph.n2v_inputs_from_networkx(graph)
-        ctx = _native.Context(getattr(self, '_device', 0))
+        from gem_b200.embedding.hope import HOPE as _H
+        dist_mod, rank, world = _H._spmd()
+        device = getattr(self, '_device', None)
+        if device is None:
+            device = int(os.environ.get('LOCAL_RANK', '0')) if world > 1 else 0
+        ctx = _native.Context(device)
         try:
+            if world > 1:
+                # SPMD: every rank holds the whole graph, walks its share of the walk index space and
+                # trains on it; the embedding deltas are all-reduced once per epoch, so every rank returns the same X
+                from gem_b200 import dist as _gd
+                _gd.init_comm_from_torch(ctx, dist_mod, rank, world)
             g = _native.DeviceGraph(ctx, csr.n, csr.indptr, csr.indices, None)
             try:
                 X, st = g.node2vec(nids, int(self._d), int(self._walk_len), int(self._num_walks),

@@ -178,8 +178,10 @@ int gemb_hope_svd_error(gemb_graph *g, int d, float beta, const float *X, int n_
 /* ---- node2vec.  Replaces the SNAP executable GEM shells out to (node2vec.py:31-48):
  * PreprocessTransitionProbs (bin@0x4127f0), node2vec() walks (bin@0x40c420),
  * LearnEmbeddings/TrainModel (bin@0x40ea30 / 0x40d6a0), WriteOutput + loadEmbedding
- * (graph_util.py:161-169).  Only p = q = 1 (first-order tables) is implemented on the GPU;
- * other values return GEMB_ERR_UNSUPPORTED.
+ * (graph_util.py:161-169).  p = q = 1 uses first-order tables (one per node); any other p, q > 0 builds the reference's
+ * second-order tables -- one alias table per directed edge (t -> v) over v's out-neighbours, sum_(t->v) outdeg(v) entries
+ * of 12 bytes -- on the device (GEMB_ERR_NOMEM with the size when they do not fit in HBM; the reference keeps the same
+ * tables in host memory).
  *
  * The graph must be uploaded single-GPU style (row0 = 0, n_local = n) with every row's column
  * ids sorted ascending (SNAP adjacency order).  weights64: fp64 edge weights in CSR order or

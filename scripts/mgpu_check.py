@@ -1,8 +1,9 @@
 """Multi-GPU equivalence check, launched with torchrun (one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P scripts/mgpu_check.py
 Checks (rank 0 prints one JSON line, exit code != 0 on failure):
-  * HOPE on a row-sharded CSR (NCCL all-gather per SpMM, all-reduce per Gram) == the same solve on one GPU
-    (sigma rtol 2e-5, reconstruction 2e-4), for the symmetric-Chebyshev and the general solver;
+  * HOPE on a row-sharded CSR == the same solve on one GPU (sigma rtol 2e-5, reconstruction 2e-3): the symmetric solvers
+    (Chebyshev subspace iteration, thick-restart Lanczos) with the needed-rows-only exchange over NVLink peer memory
+    (gem_b200/csrc/halo.cu), the general solver with the all-gather form;
   * node2vec: walk shards are the slices of the single-GPU walk matrix (bit-exact); the data-parallel SGNS
     (delta all-reduce per epoch) learns the SBM communities (nearest-neighbour purity)."""
 import json, os, sys
@@ -25,21 +26,27 @@ csr = synth.sbm(n=61_020, block=1017, seed=3)      # 61020 = 60 x 1017: not a mu
 d, beta = 32, 0.01
 r0, ip, ix, _ = csr.row_shard(rank, world)
 gsh = _native.DeviceGraph(ctx, csr.n, ip, ix, None, row0=r0)
-for algo in (2, 1):
-    Xs, sig, st = gsh.hope(d, beta, tol=1e-7, max_iters=60, min_iters=4, algorithm=algo, compute_residual=1)
+for algo in (2, 3, 1):
+    Xs, sig, st = gsh.hope(d, beta, tol=1e-7 if algo != 3 else 1e-5, max_iters=60, min_iters=4, algorithm=algo, compute_residual=int(algo != 3))
     parts = [None] * world
     dist.all_gather_object(parts, Xs)
     if rank == 0:
         X = np.concatenate(parts)[:csr.n]
         c1 = _native.Context(local)
         g1 = _native.DeviceGraph(c1, csr.n, csr.indptr, csr.indices, None)
-        X1, sig1, st1 = g1.hope(d, beta, tol=1e-7, max_iters=60, min_iters=4, algorithm=algo, compute_residual=1)
+        X1, sig1, st1 = g1.hope(d, beta, tol=1e-7 if algo != 3 else 1e-5, max_iters=60, min_iters=4, algorithm=algo, compute_residual=int(algo != 3))
         g1.free(); c1.close()
         import hope_oracle as ho
         serr = float(np.abs(sig / sig1 - 1).max()); rec = float(ho.recon_rel_err(X, X1))
         res['hope_algo%d' % algo] = dict(sigma_rel=serr, recon=rec, iters=(st['iters'], st1['iters']), resid=(st['resid_max'], st1['resid_max']),
-                                         comm_ms=st['comm_ms'], spmm_ms=st['spmm_ms'], total_ms=st['total_ms'])
-        ok &= serr < 2e-5 and rec < 2e-3 and st['resid_max'] < 1e-2 and abs(st['resid_max'] - st1['resid_max']) < 1e-4
+                                         comm_ms=st['comm_ms'], spmm_ms=st['spmm_ms'], total_ms=st['total_ms'], mg_mode=st['mg_mode'],
+                                         halo_rows=st['halo_rows'], push_rows=st['push_rows'], pushes=st['pushes'], converged=(st['converged'], st1['converged']))
+        # algorithms 2 and 3 take the needed-rows-only exchange over peer memory (mg_mode 2) unless CUDA IPC is unavailable
+        ok &= serr < 2e-5 and rec < 2e-3 and st['mg_mode'] == (1 if algo == 1 or os.environ.get('GEMB_MG') == 'allgather' else 2)
+        if algo != 3:
+            ok &= st['resid_max'] < 1e-2 and abs(st['resid_max'] - st1['resid_max']) < 1e-4
+        else:
+            ok &= st['converged'] == 1 and st1['converged'] == 1
 gsh.free()
 
 # node2vec

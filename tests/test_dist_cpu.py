@@ -143,3 +143,72 @@ def test_hope_row_sharded_gloo_equals_oracle(world):
 def test_node2vec_walk_shards_and_vocab_merge_gloo():
     ok, tok_ok, nloc = _spawn(_n2v_worker)
     assert ok and tok_ok and nloc > 0
+
+
+def _halo_worker(rank, world, port, q):
+    """The needed-rows-only exchange of gem_b200/csrc/halo.cu, host logic with gloo: every rank pushes its rows into the
+    peers' halo slots (here: point-to-point sends), then multiplies with the renumbered column ids -- the result must
+    equal the all-gather form."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from gem_b200 import synth, dist as gd
+    import scipy.sparse as sp
+    csr = synth.sbm(n=3003, block=231, seed=2)                        # 3003 rows over 2 ranks: padded last shard
+    n, b = csr.n, 8
+    n_shard = gd.rows_per_rank(n, world)
+    r0, ip, ix, _ = csr.row_shard(rank, world)
+    nl = len(ip) - 1
+    H, ext = gd.halo_plan(n, r0, n_shard, ix)
+    sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([len(H)], dtype=torch.int64))
+    maxH = int(max(s.item() for s in sizes))
+    pad = torch.full((maxH,), 2 ** 31 - 1, dtype=torch.int32)
+    pad[:len(H)] = torch.from_numpy(H)
+    allH = [torch.empty(maxH, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(allH, pad)
+    H_all = [allH[qq][:int(sizes[qq].item())].numpy() for qq in range(world)]
+    pushes = gd.push_lists(H_all, r0, n_shard, n, rank)
+    rng = np.random.default_rng(7)
+    Xfull = rng.standard_normal((n, b)).astype(np.float32)
+    Xloc = Xfull[r0:r0 + nl]
+    block = np.zeros((n_shard + len(H), b), np.float32)               # [local rows | halo]
+    block[:nl] = Xloc
+    # exchange: what the producing kernel's stores do over NVLink
+    other = 1 - rank
+    mine = [(row, slot) for row, qq, slot in pushes if qq == other]
+    send = torch.from_numpy(np.stack([Xloc[row] for row, _ in mine]) if mine else np.zeros((0, b), np.float32))
+    slots_out = torch.tensor([slot for _, slot in mine], dtype=torch.int64)
+    cnt = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(cnt, torch.tensor([len(mine)], dtype=torch.int64))
+    n_in = int(cnt[other].item())
+    recv, slots_in = torch.empty((n_in, b), dtype=torch.float32), torch.empty(n_in, dtype=torch.int64)
+    if rank == 0:
+        dist.send(send, 1); dist.send(slots_out, 1); dist.recv(recv, 1); dist.recv(slots_in, 1)
+    else:
+        dist.recv(recv, 0); dist.recv(slots_in, 0); dist.send(send, 0); dist.send(slots_out, 0)
+    block[n_shard + slots_in.numpy()] = recv.numpy()
+    assert n_in == len(H)                                            # with 2 ranks every halo row comes from the peer
+    A_ext = sp.csr_matrix((np.ones(len(ext), np.float32), ext, ip), shape=(nl, n_shard + len(H)))
+    A_glb = sp.csr_matrix((np.ones(len(ix), np.float32), ix, ip), shape=(nl, n))
+    ok = np.allclose(A_ext @ block, A_glb @ Xfull, atol=1e-5)
+    q.put((rank, bool(ok), len(H), len(pushes)))
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_equals_allgather_form():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_halo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=300) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert all(r[1] for r in res), res
+    assert all(r[2] > 0 and r[3] > 0 for r in res)

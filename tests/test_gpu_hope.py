@@ -164,7 +164,7 @@ def test_work_buffers_are_reused_between_calls(gpu_ctx):
     assert np.array_equal(X1, X3)
 
 
-@pytest.mark.parametrize('algorithm', [1, 2])
+@pytest.mark.parametrize('algorithm', [1, 2, 3])
 def test_power_law_graph_skewed_spectrum(gpu_ctx, hope_oracle, algorithm):
     """R-MAT (BASELINE configs[3] at scale 12): hubs (heavy-row SpMM path), half the nodes isolated, and with
     beta = 0.5 / rho(A) a spectrum whose k-th singular value is ~1e-2 of the first -- the convergence test must
@@ -179,6 +179,7 @@ def test_power_law_graph_skewed_spectrum(gpu_ctx, hope_oracle, algorithm):
     beta = 0.5 / rho
     m = _fresh_hope(d=16, beta=beta, tol=1e-6, max_iters=200, min_iters=4, algorithm=algorithm)
     X = m.learn_embedding(graph=csr)
+    assert m.stats['algorithm'] == algorithm and m.stats['converged'] == 1
     sig = np.asarray(m._sigma, dtype=np.float64)
     Xo, so, _ = ho.hope_sparse(A, 16, beta, tol=1e-10)
     assert so[0] < 0.1 * so[-1]                                  # the spectrum IS skewed
@@ -232,3 +233,50 @@ def test_bench_solver_setting_against_fp64_oracle(gpu_ctx, hope_oracle):
     assert max(r1.max(), r2.max()) < 1e-2
     assert orth < 1e-4
     assert abs(m.stats['resid_max'] - max(r2.max(), 0)) < 2e-3          # the library's own fp32 residual tells the truth
+
+
+def test_lanczos_on_rmat_scale16_converges_and_matches_oracle(gpu_ctx, hope_oracle):
+    """BASELINE configs[3] in small (R-MAT scale 16, 65k nodes, beta = 0.5 / rho, d = 128): the thick-restart block
+    Lanczos solver (algorithm 3; chosen automatically on such a spectrum) must CONVERGE -- round 1's filtered subspace
+    iteration ran to max_iters here -- and agree with scipy svds on the same Katz operator: every sigma to 1e-4, the
+    span of the 8 leading pairs to 0.1 degrees, fp64 residuals below 1e-3 sigma_max."""
+    import os
+    import scipy.sparse.linalg as sla
+    from gem_b200 import synth
+    ho = hope_oracle
+    csr = synth.rmat(scale=16, edge_factor=8, seed=42)
+    A = csr.to_scipy().astype(np.float64)
+    rho = float(abs(sla.eigsh(A, k=1, which='LA', return_eigenvectors=False)[0]))
+    beta = 0.5 / rho
+    d, k = 128, 64
+    m = _fresh_hope(d=d, beta=beta, tol=1e-5, max_iters=60)          # algorithm = 0: auto
+    X = m.learn_embedding(graph=csr)
+    assert m.stats['algorithm'] == 3 and m.stats['converged'] == 1, m.stats
+    sig = np.asarray(m._sigma, dtype=np.float64)
+    nthreads = min(32, os.cpu_count() or 1)
+    Xo, so, _ = ho.hope_sparse(A, d, beta, katz_tol=1e-12, tol=1e-10, threads=nthreads)
+    assert so[0] < 0.1 * so[-1]
+    assert np.allclose(sig, so, rtol=1e-4), np.abs(sig / so - 1).max()
+    assert ho.principal_angles_deg(X[:, k - 8:k], Xo[:, k - 8:k])[0] < 0.1
+    J = ho.katz_terms_needed(A, beta, 1e-12)
+    r1, r2, U, V = ho.svd_residuals(A, beta, X, J, sigma=sig)
+    assert max(r1.max(), r2.max()) < 1e-3, (r1.max(), r2.max())
+    assert np.abs(U.T @ U - np.eye(k)).max() < 1e-4
+
+
+def test_lanczos_on_the_clustered_sbm_spectrum(gpu_ctx, hope_oracle):
+    """algorithm 3 asked for explicitly on the SBM (one isolated value + a cluster): converges to a residual far below
+    what the filtered subspace iteration stops at; sigma vs scipy svds."""
+    from gem_b200 import synth
+    ho = hope_oracle
+    csr = synth.sbm(n=100_000, block=1000, seed=42)
+    m = _fresh_hope(d=128, beta=0.01, tol=1e-4, max_iters=60, algorithm=3)
+    X = m.learn_embedding(graph=csr)
+    assert m.stats['algorithm'] == 3 and m.stats['converged'] == 1
+    sig = np.asarray(m._sigma, dtype=np.float64)
+    A = csr.to_scipy()
+    Xo, so, _ = ho.hope_sparse(A, 128, 0.01, katz_tol=1e-12, tol=1e-8, threads=min(32, __import__('os').cpu_count() or 1))
+    assert np.allclose(sig, so, rtol=2e-4), np.abs(sig / so - 1).max()
+    J = ho.katz_terms_needed(A, 0.01, 1e-12)
+    r1, r2, _, _ = ho.svd_residuals(A, 0.01, X, J, sigma=sig)
+    assert max(r1.max(), r2.max()) < 5e-4

@@ -147,12 +147,56 @@ def test_hogwild_statistical_parity_sbm1024(gpu_ctx, n2v_oracle):
     assert 0.7 < np.linalg.norm(X) / np.linalg.norm(Xo) < 1.4
 
 
-def test_second_order_is_refused_loudly(gpu_ctx):
+@pytest.mark.parametrize('name,walk_len,num_walks,p,q,seed', [
+    ('karate', 20, 3, 0.5, 2.0, 7), ('symw60', 15, 3, 4.0, 0.25, 4242), ('dirw50', 12, 4, 0.7, 1.0, 99),
+    ('sbm1024', 40, 2, 1.0, 0.5, 3), ('rmat11w', 30, 2, 2.0, 3.0, 2147483646)])
+def test_second_order_walks_bit_exact(gpu_ctx, n2v_oracle, graphs, name, walk_len, num_walks, p, q, seed):
+    """p, q != 1 (node2vec.py:22-23,42-43; PreprocessNode bin@0x411f40): one alias table per directed edge (t -> v),
+    built on the device in the oracle's fp64 operation order -> walks equal the oracle's, which is pinned to the
+    unmodified binary for second-order settings too (tests/test_oracle_n2v.py, n2v_bin_*_pq.npz)."""
+    csr, nids = graphs[name]
+    g = _dev(gpu_ctx, csr)
+    W, st = g.n2v_walks(nids, walk_len, num_walks, p=p, q=q, seed=seed, weights64=csr.data)
+    Wo = n2v_oracle.walks(csr.indptr, csr.indices, csr.data, nids, walk_len, num_walks, p=p, q=q, seed=seed, mode=1)
+    assert W.shape == Wo.shape and np.array_equal(W, Wo)
+    W1 = n2v_oracle.walks(csr.indptr, csr.indices, csr.data, nids, walk_len, num_walks, seed=seed, mode=1)
+    assert not np.array_equal(Wo, W1)                               # the bias does change the walks
+    tot = len(nids) * num_walks
+    a, b = tot // 4, tot // 2 + 1
+    Ws, _ = g.n2v_walks(nids, walk_len, num_walks, p=p, q=q, seed=seed, weights64=csr.data, w_begin=a, w_end=b)
+    g.free()
+    assert np.array_equal(Ws, Wo[a:b])
+
+
+@pytest.mark.parametrize('case', ['dirw50_pq', 'symw60_pq'])
+def test_second_order_pipeline_follows_oracle_and_binary(gpu_ctx, n2v_oracle, case):
+    """The reference binary's own output for p, q != 1 (goldens made with the time() shim, OMP_NUM_THREADS=1):
+    the GPU's sequential-mode embedding follows the fp64 oracle run on the same walks, and -- on the graph without dead
+    ends, where the GPU's stream offsets are the binary's -- the binary's printed embedding itself."""
+    z = np.load(golden_path('n2v_bin_%s.npz' % case))
+    G = nx_from_npz(z)
+    csr, nids = _inputs(G)
+    hp = {k: z[k].item() for k in ('d', 'walk_len', 'num_walks', 'con_size', 'max_iter', 'seed', 'p', 'q')}
+    g = _dev(gpu_ctx, csr)
+    X, st = g.node2vec(nids, hp['d'], hp['walk_len'], hp['num_walks'], hp['con_size'], hp['max_iter'], p=hp['p'], q=hp['q'],
+                       seed=hp['seed'], sequential=True, weights64=csr.data)
+    g.free()
+    Wo = n2v_oracle.walks(csr.indptr, csr.indices, csr.data, nids, hp['walk_len'], hp['num_walks'], p=hp['p'], q=hp['q'],
+                          seed=hp['seed'], mode=1)
+    Xo, tok = n2v_oracle.learn(Wo, csr.n, hp['d'], hp['con_size'], hp['max_iter'], hp['seed'])
+    assert st['n_tokens'] == len(tok)
+    assert np.abs(X - Xo).max() < 2e-3 * np.abs(Xo).max()
+    if case == 'symw60_pq':
+        ids, emb = z['ids'], z['emb']
+        assert np.abs(X[ids] - emb).max() < 2e-3 * np.abs(emb).max()
+
+
+def test_second_order_through_the_plugin_class(gpu_ctx):
     from gem_b200.embedding.node2vec import node2vec
     node2vec.hyper_params.clear(); node2vec.hyper_params.update({'method_name': 'node2vec_rw'})
     m = node2vec(d=4, max_iter=1, walk_len=10, num_walks=2, con_size=3, ret_p=0.5, inout_p=2.0)
-    with pytest.raises(RuntimeError, match='p = q = 1'):
-        m.learn_embedding(graph=load_karate_nx())
+    X = m.learn_embedding(graph=load_karate_nx())
+    assert X.shape == (34, 4) and np.isfinite(X).all() and np.abs(X).sum() > 0
 
 
 def test_phantom_zero_and_dead_ends(gpu_ctx, n2v_oracle):
