@@ -18,8 +18,8 @@ struct ApplyTcParams {
     int64_t n;
     const float *Q;      // n x b1
     const float *M;      // b1 x b2, leading dimension ldm
-    float *Out;          // n x b2 (contiguous)
-    int b1, b2, ldm;
+    float *Out;          // n x b2, leading dimension ldo (>= b2, multiple of 4)
+    int b1, b2, ldm, ldo;
     uint32_t a_lbo;      // byte stride between 16-byte K chunks of the A tile (2048 + 16: bank-conflict free stores)
     uint32_t a_tile;     // bytes of one (hi or lo) A tile
     uint32_t b_tile;     // bytes of one (hi or lo) B tile
@@ -140,10 +140,22 @@ __global__ void __launch_bounds__(288, 1) apply_tc_kernel(ApplyTcParams p) {
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");                            // the 4 epilogue warps
-                if (tid == 0) {
-                    tc::bulk_s2g(p.Out + tile_row0(t) * p.b2, tc::smem_u32(stage), (uint32_t)tile_rows(t) * (uint32_t)p.b2 * 4u);
-                    tc::bulk_wait_read_all();                                             // staging slot may be overwritten
-                    tc::mbar_arrive(tc::smem_u32(&s_slot_free[slot]));
+                if (p.ldo == p.b2) {
+                    if (tid == 0) {
+                        tc::bulk_s2g(p.Out + tile_row0(t) * p.b2, tc::smem_u32(stage), (uint32_t)tile_rows(t) * (uint32_t)p.b2 * 4u);
+                        tc::bulk_wait_read_all();                                         // staging slot may be overwritten
+                        tc::mbar_arrive(tc::smem_u32(&s_slot_free[slot]));
+                    }
+                } else if (warp == 0) {
+                    // strided output (the two halves of X = [U sqrt(S) | V sqrt(S)], ldo = d): one bulk store per row,
+                    // four rows per lane of warp 0
+                    const int vr = tile_rows(t);
+                    float *orow = p.Out + tile_row0(t) * p.ldo;
+                    for (int r = lane; r < vr; r += 32)
+                        tc::bulk_s2g(orow + (size_t)r * p.ldo, tc::smem_u32(stage + (size_t)r * p.b2 * 4), (uint32_t)p.b2 * 4u);
+                    tc::bulk_wait_read_all();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(tc::smem_u32(&s_slot_free[slot]));
                 }
             }
         };
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(288, 1) apply_tc_kernel(ApplyTcParams p) {
             if (t >= 1) epilogue(t - 1);                                                  // overlaps the MMAs of tile t
         }
         if (nt > 0) epilogue(nt - 1);
-        if (tid == 0) tc::bulk_wait_read_all();
+        if (warp == 0) tc::bulk_wait_read_all();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -181,7 +193,7 @@ __global__ void __launch_bounds__(288, 1) apply_tc_kernel(ApplyTcParams p) {
     }
     // the bulk stores must be complete (not only read) before the kernel's results are consumed: kernel
     // completion guarantees it (bulk async-groups are flushed at exit of the issuing thread)
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <int NC16>
@@ -199,9 +211,9 @@ static int apply_tc_launch_t(gemb_ctx *ctx, const ApplyTcParams &p, int grid, si
 
 // returns GEMB_ERR_UNSUPPORTED (without setting an error) when the shape does not fit this kernel
 int apply_tc_launch(gemb_ctx *ctx, int64_t n, const float *Q, int b1, const float *M, int ldm, int b2, float *Out, int ldo) {
-    if (b1 % 8 || b2 % 4 || b1 > 128 || b2 > 128 || ldo != b2 || n <= 0) return GEMB_ERR_UNSUPPORTED;
+    if (b1 % 8 || b2 % 4 || b1 > 128 || b2 > 128 || ldo < b2 || ldo % 4 || ((uintptr_t)Out & 15) || n <= 0) return GEMB_ERR_UNSUPPORTED;
     ApplyTcParams p;
-    p.n = n; p.Q = Q; p.M = M; p.Out = Out; p.b1 = b1; p.b2 = b2; p.ldm = ldm;
+    p.n = n; p.Q = Q; p.M = M; p.Out = Out; p.b1 = b1; p.b2 = b2; p.ldm = ldm; p.ldo = ldo;
     const int widths[5] = {32, 64, 80, 96, 128};
     int npad = 128;
     for (int w : widths) if (w >= b2) { npad = w; break; }

@@ -567,13 +567,38 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
     const bool ritz_bound = nrm < 0.0;
     double bound = ritz_bound ? hard_bound * 1.02 + 1e-30 : nrm * 1.02 + 1e-30;
 
-    GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)W.g->row0, pool[0]));
-    GEMB_TRY(cholqr2(W, pool[0], pool[1], V));
-    GEMB_TRY(publish(W, V, b));
-    for (int s = 0; s < 3; s++) {   // warm-up: plain power steps V <- orth(A V) (no Rayleigh-Ritz needed yet)
-        GEMB_TRY(dist_spmm(W, false, b, 1.f, V, nullptr, AV, true));
-        GEMB_TRY(cholqr2(W, AV, pool[0], V));
+    // warm-up: V = orth(A^3 R), R Gaussian.  The three power steps run on the raw block and ONE CholeskyQR2 closes them
+    // (round 1 orthonormalised after every step: 4 x CholeskyQR2 = 3.5 ms of the 58 ms solve at S, for nothing -- the
+    // block's condition number after three steps is (lambda_1 / lambda_b)^3, a few units on a community graph).  Should
+    // the first Cholesky drop columns (skewed spectrum, rank-deficient A), the careful form below takes over.
+    bool careful = getenv("GEMB_WARMUP_CAREFUL") != nullptr;
+    if (!careful) {
+        GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)W.g->row0, pool[0]));
+        GEMB_TRY(publish(W, pool[0], b));
+        GEMB_TRY(dist_spmm3(W, false, b, 1.f, pool[0], 0.f, false, 1.f, nullptr, pool[1], true, W.halo));
+        GEMB_TRY(dist_spmm3(W, false, b, 1.f, pool[1], 0.f, false, 1.f, nullptr, pool[2], true, W.halo));
+        GEMB_TRY(dist_spmm(W, false, b, 1.f, pool[2], nullptr, AV, true));
+        GEMB_TRY(gram_full(W, AV, AV, W.G));
+        GEMB_TRY(cholqr_pass(W, W.G, AV, pool[0]));
+        int rank1 = b;
+        GEMB_CUDA(cudaMemcpyAsync(&rank1, W.rank_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        if (rank1 < b) careful = true;
+        else {
+            GEMB_TRY(gram_full(W, pool[0], pool[0], W.G));
+            GEMB_TRY(cholqr_pass(W, W.G, pool[0], V));
+            GEMB_TRY(publish(W, V, b));
+        }
+    }
+    if (careful) {
+        GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)W.g->row0, pool[0]));
+        GEMB_TRY(cholqr2(W, pool[0], pool[1], V));
         GEMB_TRY(publish(W, V, b));
+        for (int s = 0; s < 3; s++) {   // plain power steps V <- orth(A V)
+            GEMB_TRY(dist_spmm(W, false, b, 1.f, V, nullptr, AV, true));
+            GEMB_TRY(cholqr2(W, AV, pool[0], V));
+            GEMB_TRY(publish(W, V, b));
+        }
     }
 
     std::vector<double> lam(b), gval(b), th_sorted(b), th_prev(b, 0.0);

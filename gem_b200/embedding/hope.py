@@ -33,6 +33,9 @@ _OPT_KEYS = ('tol', 'max_iters', 'min_iters', 'oversample', 'katz_terms', 'katz_
              'algorithm3_basis')
 
 
+_SPMD_CTX = {}     # (device, rank, world) -> _native.Context holding the process's NCCL communicator
+
+
 def _graph_is_empty(graph):
     """`if not graph` of hope.py:25 for every accepted input type, checked in this order: HostCSR (.n), anything with a
     .shape (scipy sparse matrices AND arrays raise TypeError from __len__), then len() (networkx graphs)."""
@@ -82,14 +85,21 @@ class HOPE(StaticGraphEmbedding):
         device = getattr(self, '_device', None)
         if device is None:
             device = int(os.environ.get('LOCAL_RANK', '0')) if world > 1 else 0
-        ctx = _native.Context(device)
+        # SPMD: the context and its NCCL communicator are created once per process and kept (communicator set-up costs
+        # 0.5-1 s -- ten times the solve); single GPU: a context is a stream + a few small buffers, made per call
+        ctx = _SPMD_CTX.get((device, rank, world)) if world > 1 else None
+        fresh = ctx is None
+        if fresh:
+            ctx = _native.Context(device)
         try:
             if world > 1:
-                # SPMD contract: every rank calls learn_embedding with the same graph (or with its
-                # own row shard as a (row0, HostCSR-of-the-shard, n) triple); the library communicator is bootstrapped
-                # through the already initialised torch.distributed group; the call returns THIS rank's rows of X.
-                from gem_b200 import dist as _gd
-                _gd.init_comm_from_torch(ctx, dist_mod, rank, world)
+                # SPMD contract: every rank calls learn_embedding with the same graph; the library
+                # communicator is bootstrapped through the already initialised torch.distributed group; the call
+                # returns THIS rank's rows of X.
+                if fresh:
+                    from gem_b200 import dist as _gd
+                    _gd.init_comm_from_torch(ctx, dist_mod, rank, world)
+                    _SPMD_CTX[(device, rank, world)] = ctx
                 if not csr.is_symmetric():
                     r0, ip, ix, dat = csr.row_shard(rank, world)
                     t = csr.transpose()
@@ -122,7 +132,8 @@ class HOPE(StaticGraphEmbedding):
             finally:
                 g.free()
         finally:
-            ctx.close()
+            if world == 1:
+                ctx.close()
         self.stats = st
         self._sigma = sigma
         self._node_num = csr.n

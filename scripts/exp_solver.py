@@ -16,6 +16,8 @@ for deg, rng, osamp in itertools.product((8, 10, 12, 16), (8, 14, 20), (8, 16)):
         if deg == 8 and rng == 8 and osamp == 16 and stop == 0:
             continue
         grid.append(dict(tol=tol, oversample=osamp, cheb_degree=deg, cheb_range_log2=rng, stop_rule=stop))
+for basis in (0, 128, 192):
+    grid.append(dict(tol=1e-3, oversample=16, algorithm=3, algorithm3_basis=basis))
 out = open(os.path.join('gpurun_out', 'exp_solver.jsonl'), 'w')
 g.hope(128, 0.01, want_output=False, **base, **grid[0])           # warm-up
 for cfg in grid:
@@ -24,7 +26,10 @@ for cfg in grid:
         _, _, st = g.hope(128, 0.01, want_output=False, **base, **cfg)
         if best is None or st['total_ms'] < best['total_ms']:
             best = st
-    _, _, sr = g.hope(128, 0.01, want_output=False, compute_residual=1, **base, **cfg)
+    try:
+        _, _, sr = g.hope(128, 0.01, want_output=False, compute_residual=1, **base, **cfg)
+    except RuntimeError as exc:
+        sr = {'resid_max': str(exc)}
     rec = dict(cfg, iters=best['iters'], converged=best['converged'], sweeps=best['spmm_count'], total_ms=round(best['total_ms'], 2),
                spmm_ms=round(best['spmm_ms'], 2), dense_ms=round(best['dense_ms'], 2), block=best['block'],
                ritz_change=best['ritz_change'], resid_est=best['resid_est'], resid_max=sr['resid_max'])
