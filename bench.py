@@ -171,6 +171,26 @@ def cpu_hope_sample(n_sample, d, beta, tol, seed=42, A=None):
     return A.shape[0] / dt, dt, info
 
 
+def cpu_hope_rmat_sample(scale, d, beta_over_rho):
+    """CPU arm of the R-MAT workload on a bounded sample: the host generator's R-MAT at `scale` (same family, seed 42),
+    beta = beta_over_rho / rho(A) (rho from scipy eigsh), scipy svds(tol=1e-3) over the matrix-free Katz operator."""
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import hope_oracle as ho
+    import scipy.sparse.linalg as sla
+    from gem_b200 import synth
+    A = synth.rmat(scale=scale, seed=42).to_scipy().astype(np.float64)
+    rho = float(abs(sla.eigsh(A, k=1, which='LA', return_eigenvectors=False)[0]))
+    beta = beta_over_rho / rho
+    threads, calib = pick_katz_threads(ho, A, beta)
+    t = time.perf_counter()
+    X, s_, info = ho.hope_sparse(A, d, beta, katz_tol=1e-7, tol=CPU_ARPACK_TOL, threads=threads)
+    dt = time.perf_counter() - t
+    return {'value': A.shape[0] / dt, 'unit': 'nodes/s', 'cores': threads, 'kind': 'port', 'host_cores': os.cpu_count(), 'seconds': dt,
+            'sample': 'R-MAT scale %d (host generator, seed 42), d=%d, beta=%g/rho=%.6g: scipy svds(tol=%g, ARPACK) over the matrix-free '
+                      'fp64 Katz operator on %d OpenMP threads, J=%d, %d SpMVs' % (scale, d, beta_over_rho, beta, CPU_ARPACK_TOL, threads,
+                                                                                  info['katz_terms'], info['spmv'])}
+
+
 def pick_katz_threads(ho, A, beta):
     """Thread count of the OpenMP Katz operator for the CPU arm: the fastest of {1, 2, 4, ... , usable cores} on THIS
     matrix, each timed over a few operator applications interleaved with a BLAS product on an n x 32 block (ARPACK's own
@@ -214,12 +234,13 @@ REFERENCE_CLASS_TIMINGS = {'where': 'build container, 8 host cores, gem.embeddin
                            'n=4096': {'seconds': 11.4, 'nodes_per_s': 360}, 'n=8192': {'seconds': 53.6, 'nodes_per_s': 153}}
 
 
-def cpu_n2v_sample(n_sample, d, walk_len, num_walks, con_size, threads):
+def cpu_n2v_sample(n_sample, d, walk_len, num_walks, con_size, threads, csr=None):
     """node2vec on the host: the reference's SNAP binary (oracle/_ref/node2vec, all threads) when it is
     present, else our single-threaded C restatement.  Returns (nodes/s, seconds, kind, cores)."""
     import tempfile
     from gem_b200 import synth
-    csr = synth.sbm(n=n_sample, block=min(1000, n_sample), seed=42)
+    if csr is None:
+        csr = synth.sbm(n=n_sample, block=min(1000, n_sample), seed=42)
     exe = os.path.join(REPO, 'oracle/_ref/node2vec')
     if os.path.exists(exe):
         with tempfile.TemporaryDirectory() as td:
@@ -338,6 +359,18 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ----------------------------------------------------------------------------------- graphs
+def rmat_rows(n, rank, world):
+    per = (n + world - 1) // world
+    r0 = min(n, rank * per)
+    return r0, min(n, r0 + per) - r0
+
+
+def rmat_name(args):
+    return ('R-MAT scale %d (Graph500 a,b,c,d = .57,.19,.19,.05, edge factor 8, vertices permuted, symmetrised, loops and '
+            'duplicates removed; generated on the device by gemb_synth_rmat, counter-based RNG seed 42)' % args.scale)
+
 # ----------------------------------------------------------------------------------- our arm
 def hope_workload_name(d, beta, n, world):
     return ('HOPE d=%d beta=%g on SBM n=%d (%d per GPU), ~20 directed edges per node, 1000-node blocks, '
@@ -397,25 +430,44 @@ def run_hope(args, dist, rank, world, local):
     from gem_b200 import _native, synth
     from gem_b200.embedding.hope import HOPE
     peaks, peak_src = read_peaks()
-    n = args.n * world                                   # weak scaling: rows per GPU fixed
-    t0 = time.perf_counter()
-    csr = synth.sbm(n=n, block=1000, seed=42)            # host, not timed
-    gen_s = time.perf_counter() - t0
+    rmat = args.graph == 'rmat'
     ctx = _native.Context(local)
     if world > 1:
         uid = [_native.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
-    r0, ip, ix, _ = csr.row_shard(rank, world)
-    g = _native.DeviceGraph(ctx, csr.n, ip, ix, None, row0=r0)
+    t0 = time.perf_counter()
+    if rmat:
+        # BASELINE.json configs[3]: the graph is FIXED (scale 24 = 16.7M nodes on 8 GPUs): strong scaling in N.
+        # Every rank generates the graph on its own GPU (identical by construction) and keeps its row shard.
+        from gem_b200.graph import HostCSR
+        n = 1 << args.scale
+        r0, rows = rmat_rows(n, rank, world)
+        ip, ix, nnz_total = _native.synth_rmat(ctx, args.scale, seed=42, row0=r0, n_rows=rows)
+        csr = HostCSR(n, ip, ix, None, symmetric=True) if world == 1 else None
+        n_all, nnz_all = n, nnz_total
+    else:
+        n = args.n * world                                   # weak scaling: rows per GPU fixed
+        csr = synth.sbm(n=n, block=1000, seed=42)            # host, not timed
+        r0, ip, ix, _ = csr.row_shard(rank, world)
+        n_all, nnz_all = csr.n, csr.nnz
+    gen_s = time.perf_counter() - t0
+    g = _native.DeviceGraph(ctx, n_all, ip, ix, None, row0=r0)
+    n_own_rows = len(ip) - 1
     solver = dict(HOPE_SOLVER)
+    beta_arg = args.beta
+    if rmat:
+        # skewed spectrum: the auto rule hands the solve to the thick-restart block Lanczos solver (algorithm 3), whose
+        # stopping test is the Ritz residual mapped to the Katz operator, relative to sigma_max
+        solver = dict(tol=1e-3, max_iters=60, oversample=16, seed=1234)
+        beta_arg = -args.beta_over_rho                       # beta = 0.5 / rho_hat(A), rho_hat by power iteration in the call
     if args.tol is not None:
         solver['tol'] = args.tol
     if args.max_iters is not None:
         solver['max_iters'] = args.max_iters
 
     for _ in range(args.warmup):
-        g.hope(args.d, args.beta, want_output=False, **solver)
+        g.hope(args.d, beta_arg, want_output=False, **solver)
     dist_barrier(dist, local)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -424,7 +476,7 @@ def run_hope(args, dist, rank, world, local):
     dev_ms, stats = 0.0, None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, _, st = g.hope(args.d, args.beta, want_output=False, **solver)
+        _, _, st = g.hope(args.d, beta_arg, want_output=False, **solver)
         dev_ms += st['total_ms']
         stats = st if stats is None else {k: (stats[k] + st[k] if k in ('spmm_ms', 'dense_ms', 'comm_ms', 'spmm_count', 'pushes') else st[k])
                                           for k in st}
@@ -434,13 +486,13 @@ def run_hope(args, dist, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = dist_max(dist, dev_ms, local)
     wall_s = dist_max(dist, wall_s, local)
-    value = n * args.steps / (dev_ms * 1e-3)
+    value = n_all * args.steps / (dev_ms * 1e-3)
 
     # accuracy of the timed solution, outside the timed region: one more identical solve that also applies the fp32
     # Katz operator to the result, || S^T u_j - sigma_j v_j || / sigma_max over the k triplets (collective on N > 1)
     resid_max = None
     try:
-        _, _, st_r = g.hope(args.d, args.beta, want_output=False, compute_residual=1, **solver)
+        _, _, st_r = g.hope(args.d, beta_arg, want_output=False, compute_residual=1, **solver)
         resid_max = float(st_r['resid_max'])
     except Exception as exc:                                   # diagnostics only: never fail the bench line
         resid_max = 'unavailable: %s' % exc
@@ -466,14 +518,15 @@ def run_hope(args, dist, rank, world, local):
     # row shard, and reads back ITS rows of X; the step time is the max over ranks of the host clock around the call.
     e2e = None
     accuracy = None
-    if not args.no_e2e:
+    if not args.no_e2e and csr is not None:
         g.free()
         g = None
         hc = pinned_csr(csr)
         n_own = len(csr.row_shard(rank, world)[1]) - 1
         out = _native.pinned_empty((n_own, args.d), np.float32)
         HOPE.hyper_params.clear(); HOPE.hyper_params.update({'method_name': 'hope_gsvd'})
-        model = HOPE(d=args.d, beta=args.beta, device=local, svd_error_probes=False, **solver)
+        extra = dict(beta_over_rho=args.beta_over_rho) if rmat else {}
+        model = HOPE(d=args.d, beta=args.beta, device=local, svd_error_probes=False, strict=False, **extra, **solver)
         model.learn_embedding(graph=hc, out=out)                      # warm-up
         # K plugin calls, each timed on the host clock around the whole call (H2D of the CSR, solve, D2H of X).
         # The GPU boxes show bursts of host-side stalls (a 9 ms D2H wait returning after 600 ms, with the device
@@ -498,18 +551,21 @@ def run_hope(args, dist, rank, world, local):
                'call': 'gem_b200.embedding.hope.HOPE(d, beta).learn_embedding(graph=<CSR in pinned host memory>)'
                        + (' on every rank (SPMD, rows of X per rank)' if world > 1 else '')}
         if world == 1 and not args.no_accuracy:
-            accuracy = fp64_accuracy_of_solution(csr, np.asarray(X), model._sigma, args.beta)
+            accuracy = fp64_accuracy_of_solution(csr, np.asarray(X), model._sigma, float(model._beta), katz_terms=40 if rmat else 14)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        n_s = args.cpu_sample or 100000
-        v, dt, info = cpu_hope_sample(n_s, args.d, args.beta, CPU_ARPACK_TOL)
-        cpu = {'value': v, 'unit': 'nodes/s', 'cores': info['threads'], 'kind': 'port', 'host_cores': os.cpu_count(),
-               'seconds': dt,
-               'sample': 'SBM n=%d (same density, seed 42), d=%d, beta=%g: scipy svds(tol=%g, ARPACK) over the matrix-free fp64 '
-                         'Katz operator (oracle/hope_oracle.hope_sparse, operator on %d OpenMP threads), J=%d, %d SpMVs; the '
-                         'full 1M-node solve is what `--impl reference` times' % (
-                             n_s, args.d, args.beta, CPU_ARPACK_TOL, info['threads'], info['katz_terms'], info['spmv'])}
+        if rmat:
+            cpu = cpu_hope_rmat_sample(args.cpu_rmat_scale, args.d, args.beta_over_rho)
+        else:
+            n_s = args.cpu_sample or 100000
+            v, dt, info = cpu_hope_sample(n_s, args.d, args.beta, CPU_ARPACK_TOL)
+            cpu = {'value': v, 'unit': 'nodes/s', 'cores': info['threads'], 'kind': 'port', 'host_cores': os.cpu_count(),
+                   'seconds': dt,
+                   'sample': 'SBM n=%d (same density, seed 42), d=%d, beta=%g: scipy svds(tol=%g, ARPACK) over the matrix-free fp64 '
+                             'Katz operator (oracle/hope_oracle.hope_sparse, operator on %d OpenMP threads), J=%d, %d SpMVs; the '
+                             'full 1M-node solve is what `--impl reference` times' % (
+                                 n_s, args.d, args.beta, CPU_ARPACK_TOL, info['threads'], info['katz_terms'], info['spmv'])}
     if g is not None:
         g.free()
     line = None
@@ -519,9 +575,11 @@ def run_hope(args, dist, rank, world, local):
                  'producing kernel; b x b Gram all-reduce on NCCL' % world}[stats.get('mg_mode', 0)]
         line = {'metric': 'nodes/sec embedded at d=128', 'value': value, 'unit': 'nodes/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
-                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'higher_is_better': True, 'scaling': 'strong' if rmat else 'weak', 'vs_baseline': None, 'dtype': 'f32',
                 'data': 'synthetic',
-                'config': {'workload': hope_workload_name(args.d, args.beta, n, world), 'nnz': csr.nnz,
+                'config': {'workload': ('HOPE d=%d beta=%g/rho_hat(A) = %.6g on %s: n=%d' % (args.d, args.beta_over_rho, stats.get('beta_used', 0.0), rmat_name(args), n_all))
+                                       if rmat else hope_workload_name(args.d, args.beta, n, world), 'nnz': nnz_all,
+                           'rho_hat': (args.beta_over_rho / stats['beta_used']) if rmat and stats.get('beta_used') else None,
                            'solver': dict(solver, block=stats['block'], katz_terms=stats['katz_terms'],
                                           iters=stats['iters'], converged=stats['converged'],
                                           ritz_change=stats['ritz_change'], resid_max_rel_sigma_max=resid_max,
@@ -535,7 +593,7 @@ def run_hope(args, dist, rank, world, local):
                                                                 'blocks_exchanged_per_step': stats.get('pushes', 0) / args.steps,
                                                                 'nvlink_bytes_out_per_step_rank0': stats.get('pushes', 0) / args.steps * stats.get('push_rows', 0) * 4 * stats['block']},
                            'l2_policy': 'inputs larger than L2 (CSR %.0f MB + 5 blocks of %.0f MB vs 126 MB L2)' % (
-                               (csr.nnz * 4 + csr.n * 4) / 1e6, csr.n * stats['block'] * 4 / 1e6 / world)},
+                               (nnz_all * 4 + n_all * 4) / 1e6 / world, n_all * stats['block'] * 4 / 1e6 / world)},
                 'wall_ms_per_step': wall_s * 1e3 / args.steps, 'graph_gen_s': gen_s,
                 'phases_ms_per_step': {'spmm': stats['spmm_ms'] / args.steps, 'dense': stats['dense_ms'] / args.steps,
                                        'comm': stats['comm_ms'] / args.steps},
@@ -556,14 +614,26 @@ def run_node2vec(args, dist, rank, world, local):
     from gem_b200 import _native, synth
     from gem_b200.embedding.node2vec import node2vec
     peaks, peak_src = read_peaks()
-    n = args.n * world
-    csr = synth.sbm(n=n, block=1000, seed=42)
-    nids = np.arange(csr.n, dtype=np.int32)
+    rmat = args.graph == 'rmat'
     ctx = _native.Context(local)
     if world > 1:
         uid = [_native.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
+    if rmat:
+        # BASELINE.json configs[4]: the whole graph replicated on every GPU (generated there), walk starts sharded.
+        # Half of an R-MAT's vertices have no edge at all: like the reference (whose edge-list file never mentions them)
+        # only vertices with edges are in the node table, get walks and count as embedded.
+        from gem_b200.graph import HostCSR
+        n = 1 << args.scale
+        ip, ix, _tot = _native.synth_rmat(ctx, args.scale, seed=42)
+        csr = HostCSR(n, ip, ix, None, symmetric=True)
+        nids = np.flatnonzero(np.diff(ip) > 0).astype(np.int32)
+    else:
+        n = args.n * world
+        csr = synth.sbm(n=n, block=1000, seed=42)
+        nids = np.arange(csr.n, dtype=np.int32)
+    n_emb = int(nids.shape[0])
     g = _native.DeviceGraph(ctx, csr.n, csr.indptr, csr.indices, None)
     hp = (args.d, args.walk_len, args.num_walks, args.con_size, 1)
     # warm-up: full-size steps are ~10 s each; warm the kernels on short walks of the same graph
@@ -584,7 +654,7 @@ def run_node2vec(args, dist, rank, world, local):
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = dist_max(dist, dev_ms, local)
     pairs = dist_sum(dist, float(agg['pairs']), local)
-    value = n * args.steps / (dev_ms * 1e-3)
+    value = n_emb * args.steps / (dev_ms * 1e-3)
     sg_bytes = pairs * 14 * 4 * args.d
     achieved = sg_bytes / world / (agg['sgns_ms'] * 1e-3) / 1e9 if agg['sgns_ms'] > 0 else 0.0
     roofline = {'kernel': 'sgns (warp per walk, fp32 tables)', 'bound': 'hbm', 'achieved': achieved,
@@ -602,29 +672,35 @@ def run_node2vec(args, dist, rank, world, local):
         X = model.learn_embedding(graph=(csr, nids))
         _ = float(X[0, 0])
         e2e_s = time.perf_counter() - t0
-        e2e = {'value': csr.n / e2e_s, 'unit': 'nodes/s', 'ms_per_step': e2e_s * 1e3,
-               'h2d_bytes_per_step': int(4 * (csr.n + 1) + 4 * csr.nnz + 4 * csr.n * args.num_walks),
+        e2e = {'value': n_emb / e2e_s, 'unit': 'nodes/s', 'ms_per_step': e2e_s * 1e3,
+               'h2d_bytes_per_step': int(4 * (csr.n + 1) + 4 * csr.nnz + 4 * n_emb * args.num_walks),
                'd2h_bytes_per_step': int(4 * csr.n * args.d), 'steps': 1,
                'call': 'gem_b200.embedding.node2vec.node2vec(...).learn_embedding(graph=(CSR, node table))'}
     cpu = None
     if rank == 0 and not args.no_cpu:
         n_s = args.n2v_cpu_sample or 2000
-        v, dt, kind, used = cpu_n2v_sample(n_s, args.d, args.walk_len, args.num_walks, args.con_size, os.cpu_count() or 1)
+        scsr = None
+        if rmat:
+            scsr = synth.rmat(scale=11, seed=42)
+            n_s = int((np.diff(scsr.indptr) > 0).sum())
+        v, dt, kind, used = cpu_n2v_sample(n_s, args.d, args.walk_len, args.num_walks, args.con_size, os.cpu_count() or 1, csr=scsr)
         cpu = {'value': v, 'unit': 'nodes/s', 'cores': used, 'kind': kind, 'host_cores': os.cpu_count(), 'seconds': dt,
-               'sample': 'SBM n=%d (same density, seed 42), d=%d r=%d l=%d k=%d e=1 p=q=1 (%s)' % (
-                   n_s, args.d, args.num_walks, args.walk_len, args.con_size,
+               'sample': '%s, d=%d r=%d l=%d k=%d e=1 p=q=1 (%s)' % (
+                   ('R-MAT scale 11 (host generator, seed 42; %d vertices with edges -- the reference binary builds one alias '
+                    'table per directed edge, sum deg^2 entries: it cannot hold scale 24)' % n_s) if rmat
+                   else 'SBM n=%d (same density, seed 42)' % n_s, args.d, args.num_walks, args.walk_len, args.con_size,
                    'gem/c_exe/node2vec, OMP threads = cores' if kind == 'reference' else 'oracle/n2v_oracle.c, 1 thread')}
     g.free()
     line = None
     if rank == 0:
         line = {'metric': 'nodes/sec embedded at d=128', 'value': value, 'unit': 'nodes/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
-                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': 'node2vec d=%d p=q=1, %d walks x %d, context %d, 1 epoch, 5 negatives, on SBM n=%d, nnz=%d'
-                                       % (args.d, args.num_walks, args.walk_len, args.con_size, n, csr.nnz),
+                'higher_is_better': True, 'scaling': 'strong' if rmat else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': 'node2vec d=%d p=q=1, %d walks x %d, context %d, 1 epoch, 5 negatives, on %s n=%d, nnz=%d; %d vertices have edges (node table, walks, value)'
+                                       % (args.d, args.num_walks, args.walk_len, args.con_size, rmat_name(args) if rmat else 'SBM', n, csr.nnz, n_emb),
                            'parallelism': 'walk-sharded x%d, embedding-delta all-reduce per epoch' % world if world > 1 else 'single GPU',
                            'l2_policy': 'inputs larger than L2 (two %d MB embedding tables + %d MB walks)' % (
-                               csr.n * args.d * 4 // 10**6, csr.n * args.num_walks * args.walk_len * 4 // 10**6)},
+                               csr.n * args.d * 4 // 10**6, n_emb * args.num_walks * args.walk_len * 4 // 10**6 // world)},
                 'phases_ms_per_step': {k: agg[k] / args.steps for k in ('alias_ms', 'shuffle_ms', 'walk_ms', 'vocab_ms', 'sgns_ms', 'comm_ms')},
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'e2e': e2e, 'cpu_baseline': cpu}
     ctx.close()
@@ -732,6 +808,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='hope', choices=['hope', 'node2vec', 'recon'])
     ap.add_argument('--n', type=int, default=1_000_000, help='nodes per GPU')
+    ap.add_argument('--graph', default='sbm', choices=['sbm', 'rmat'], help='rmat: BASELINE.json configs[3]/[4] (fixed graph, --scale)')
+    ap.add_argument('--scale', type=int, default=24, help='R-MAT scale (2^scale nodes, 8 * 2^scale undirected pairs)')
+    ap.add_argument('--beta-over-rho', type=float, default=0.5, help='R-MAT HOPE: beta = this / rho_hat(A)')
+    ap.add_argument('--cpu-rmat-scale', type=int, default=14, help='R-MAT scale of the CPU baseline sample')
     ap.add_argument('--d', type=int, default=128)
     ap.add_argument('--beta', type=float, default=0.01)
     ap.add_argument('--tol', type=float, default=None)
@@ -758,7 +838,7 @@ def main():
     try:
         if args.workload == 'hope':
             line = run_hope(args, dist, rank, world, local)
-            if not args.no_node2vec:
+            if not args.no_node2vec and args.graph != 'rmat':
                 # BASELINE.json configs[2] rides in the same line (one epoch = one step; it takes ~10 s, so it is timed
                 # once whatever --steps says): the driver's bench and scaling runs then see node2vec too
                 steps, warm = args.steps, args.warmup

@@ -19,7 +19,7 @@ EXPORTS = [
     'gemb_host_alloc', 'gemb_host_free', 'gemb_mem_trim', 'gemb_mem_cached_bytes', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
     'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_apply', 'gemb_hope', 'gemb_hope_svd_error', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
     'gemb_edge_list_scan', 'gemb_edge_list_parse', 'gemb_edge_list_write', 'gemb_emb_read', 'gemb_emb_write',
-    'gemb_recon_create', 'gemb_recon_free', 'gemb_recon_dense', 'gemb_recon_pairs', 'gemb_recon_ranks', 'gemb_recon_top',
+    'gemb_synth_rmat', 'gemb_recon_create', 'gemb_recon_free', 'gemb_recon_dense', 'gemb_recon_pairs', 'gemb_recon_ranks', 'gemb_recon_top',
 ]
 
 
@@ -40,7 +40,8 @@ class HopeStats(ctypes.Structure):
                 ('comm_ms', ctypes.c_double), ('total_ms', ctypes.c_double), ('h2d_ms', ctypes.c_double),
                 ('d2h_ms', ctypes.c_double), ('norm2_A', ctypes.c_float), ('ritz_change', ctypes.c_float),
                 ('resid_max', ctypes.c_float), ('resid_est', ctypes.c_float), ('mg_mode', ctypes.c_int32),
-                ('halo_rows', ctypes.c_int64), ('push_rows', ctypes.c_int64), ('pushes', ctypes.c_int64)]
+                ('halo_rows', ctypes.c_int64), ('push_rows', ctypes.c_int64), ('pushes', ctypes.c_int64),
+                ('beta_used', ctypes.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'struct_size'}
@@ -100,6 +101,8 @@ def lib():
     L.gemb_edge_list_write.argtypes = [cp, i64, vp, vp, vp, i64]
     L.gemb_emb_read.argtypes = [cp, ctypes.POINTER(i64), ctypes.POINTER(i32), vp]
     L.gemb_emb_write.argtypes = [cp, i64, vp, i32, vp, i64]
+    L.gemb_synth_rmat.argtypes = [vp, ctypes.c_int, ctypes.c_int, f64, f64, f64, ctypes.c_uint64, ctypes.c_int, i64, i64,
+                                  ctypes.POINTER(i64), ctypes.POINTER(i64), vp, vp, i64]
     L.gemb_recon_create.argtypes = [vp, vp, i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     L.gemb_recon_free.argtypes = [vp]
     L.gemb_recon_dense.argtypes = [vp, vp]
@@ -199,6 +202,19 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def synth_rmat(ctx, scale, edge_factor=8, a=0.57, b=0.19, c=0.19, seed=42, permute=True, row0=0, n_rows=-1):
+    """Device R-MAT generator (gemb_synth_rmat): (indptr int64 shard-local, indices int32 global ids, nnz of the whole graph)
+    of rows [row0, row0 + n_rows) -- all rows when n_rows < 0."""
+    nnz, tot = ctypes.c_int64(0), ctypes.c_int64(0)
+    args = (ctx._h, int(scale), int(edge_factor), float(a), float(b), float(c), int(seed), int(bool(permute)), int(row0), int(n_rows))
+    check(lib().gemb_synth_rmat(*args, ctypes.byref(nnz), ctypes.byref(tot), None, None, 0))
+    rows = (1 << scale) if n_rows < 0 else int(n_rows)
+    indptr = np.empty(rows + 1, dtype=np.int64)
+    indices = np.empty(max(int(nnz.value), 1), dtype=np.int32)
+    check(lib().gemb_synth_rmat(*args, ctypes.byref(nnz), ctypes.byref(tot), _ptr(indptr), _ptr(indices), int(indices.shape[0])))
+    return indptr, indices[:int(nnz.value)], int(tot.value)
 
 
 def comm_unique_id():

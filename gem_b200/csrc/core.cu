@@ -300,14 +300,14 @@ static int upload_csr(gemb_ctx *c, int64_t n, int64_t n_local, const int32_t *in
     GEMB_ARG(nnz >= 0 && nnz < (int64_t)2147483647, "nnz per shard must be < 2^31");
     d->nnz = nnz;
     GEMB_CUDA(dmalloc(&d->indptr, sizeof(int32_t) * (n_local + 1)));
-    GEMB_CUDA(dmalloc(&d->indices, sizeof(int32_t) * (nnz > 0 ? nnz : 1)));
+    GEMB_CUDA(dmalloc(&d->indices, sizeof(int32_t) * ((nnz > 0 ? nnz : 1) + 4)));
     GEMB_CUDA(cudaMemcpyAsync(d->indptr, indptr, sizeof(int32_t) * (n_local + 1),
                               cudaMemcpyHostToDevice, c->stream));
     if (nnz)
         GEMB_CUDA(cudaMemcpyAsync(d->indices, indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice,
                                   c->stream));
     if (data && nnz) {
-        GEMB_CUDA(dmalloc(&d->data, sizeof(float) * nnz));
+        GEMB_CUDA(dmalloc(&d->data, sizeof(float) * (nnz + 4)));
         GEMB_CUDA(cudaMemcpyAsync(d->data, data, sizeof(float) * nnz, cudaMemcpyHostToDevice,
                                   c->stream));
     }

@@ -545,9 +545,13 @@ eigh_jacobi_kernel(int b, double *__restrict__ Ag, double *__restrict__ w, doubl
 //   * the eigenvector accumulator is kept transposed so that its update is a row walk;
 //   * (pair, column) indices advance incrementally (no division in the loops), rotation parameters are one
 //     16-byte and one 8-byte load, the leading dimension is odd (conflict-free row and column walks).
+// ZT_GLOBAL (112 < b <= 164, the Rayleigh-Ritz matrix of the thick-restart Lanczos solver): A alone fills the shared
+// memory, the eigenvector accumulator lives in global memory (L2 resident, 200 KB) and is updated by coalesced row
+// walks -- the generic MODE 1 kernel needed 15.2 ms for b = 160 (10.9 us per Jacobi round, 43 % of an R-MAT solve).
+template <bool ZT_GLOBAL>
 __global__ void __launch_bounds__(1024)
 eigh_jacobi_fast_kernel(int b, const double *__restrict__ Ag, double *__restrict__ w, double *__restrict__ Z,
-                        int max_sweeps, double rel_tol) {
+                        double *__restrict__ Ztg, int max_sweeps, double rel_tol) {
     extern __shared__ __align__(16) unsigned char sh_fast[];
     double *sh = (double *)sh_fast;
     const int m = (b + 1) & ~1;
@@ -556,13 +560,14 @@ eigh_jacobi_fast_kernel(int b, const double *__restrict__ Ag, double *__restrict
     double2 *csn = (double2 *)sh;                 // half : (c, s)
     int2 *pq = (int2 *)(sh + 2 * half);           // half : (p, q), q = -1 for the dummy partner
     double *A = sh + 3 * half + 2;                // b x ld
-    double *ZT = A + (size_t)b * ld;              // ZT[j][k] = component k of eigenvector j
+    double *ZT = ZT_GLOBAL ? Ztg : A + (size_t)b * ld;   // ZT[j][k] = component k of eigenvector j
+    const int ldz = ZT_GLOBAL ? b : ld;
     __shared__ double s_off, s_diag;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int idx = tid; idx < b * b; idx += nt) {
         const int i = idx / b, j = idx - i * b;
         A[i * ld + j] = Ag[idx];
-        ZT[i * ld + j] = (i == j) ? 1.0 : 0.0;
+        ZT[i * ldz + j] = (i == j) ? 1.0 : 0.0;
     }
     // incremental (pair, column) walks: idx = tid + t * nt  ->  (idx / div, idx % div)
     const int zb_i0 = tid / b, zb_k0 = tid - zb_i0 * b, zb_di = nt / b, zb_dk = nt - zb_di * b;
@@ -629,17 +634,50 @@ eigh_jacobi_fast_kernel(int b, const double *__restrict__ Ag, double *__restrict
                 if (rj >= half) { rj -= half; pi++; }
             }
             // Z^T <- J^T Z^T (rows p, q; consecutive threads = consecutive columns)
-            for (int pi = zb_i0, k = zb_k0; pi < half;) {
-                const double2 rt = csn[pi];
-                const int2 a = pq[pi];
-                if (a.y >= 0 && rt.y != 0.0) {
-                    double *xp = ZT + a.x * ld + k, *yp = ZT + a.y * ld + k;
-                    const double x = *xp, y = *yp;
-                    *xp = rt.x * x - rt.y * y;
-                    *yp = rt.y * x + rt.x * y;
+            if (ZT_GLOBAL) {
+                // global (L2) accumulator: batches of 4 independent element pairs -- all 8 loads are issued before the
+                // first store, otherwise every element pays a full L2 round trip in sequence
+                int pi = zb_i0, k = zb_k0;
+                while (pi < half) {
+                    double *xp[4], *yp[4];
+                    double2 rt[4];
+                    double x[4], y[4];
+                    bool on[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        on[u] = false;
+                        if (pi < half) {
+                            rt[u] = csn[pi];
+                            const int2 a = pq[pi];
+                            if (a.y >= 0 && rt[u].y != 0.0) {
+                                on[u] = true;
+                                xp[u] = ZT + a.x * ldz + k; yp[u] = ZT + a.y * ldz + k;
+                            }
+                            k += zb_dk; pi += zb_di;
+                            if (k >= b) { k -= b; pi++; }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) if (on[u]) { x[u] = __ldcg(xp[u]); y[u] = __ldcg(yp[u]); }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) if (on[u]) {
+                        __stcg(xp[u], rt[u].x * x[u] - rt[u].y * y[u]);
+                        __stcg(yp[u], rt[u].y * x[u] + rt[u].x * y[u]);
+                    }
                 }
-                k += zb_dk; pi += zb_di;
-                if (k >= b) { k -= b; pi++; }
+            } else {
+                for (int pi = zb_i0, k = zb_k0; pi < half;) {
+                    const double2 rt = csn[pi];
+                    const int2 a = pq[pi];
+                    if (a.y >= 0 && rt.y != 0.0) {
+                        double *xp = ZT + a.x * ldz + k, *yp = ZT + a.y * ldz + k;
+                        const double x = *xp, y = *yp;
+                        *xp = rt.x * x - rt.y * y;
+                        *yp = rt.y * x + rt.x * y;
+                    }
+                    k += zb_dk; pi += zb_di;
+                    if (k >= b) { k -= b; pi++; }
+                }
             }
             __syncthreads();
         }
@@ -655,7 +693,7 @@ eigh_jacobi_fast_kernel(int b, const double *__restrict__ Ag, double *__restrict
         }
         for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
         if (lane == 0) w[rank] = wj;
-        for (int k = lane; k < b; k += 32) Z[(size_t)k * b + rank] = ZT[j * ld + k];
+        for (int k = lane; k < b; k += 32) Z[(size_t)k * b + rank] = ZT_GLOBAL ? __ldcg(ZT + j * ldz + k) : ZT[j * ldz + k];
     }
 }
 
@@ -666,13 +704,16 @@ int eigh_launch(gemb_ctx *ctx, int b, double *G, double *w, double *Z, double *Z
     const size_t cap = 220 * 1024;
     static const bool generic_only = getenv("GEMB_DENSE_GENERIC") != nullptr;
     const size_t fast = base + 2 * sizeof(double) * (size_t)b * (b | 1);
-    if (fast <= cap && !generic_only) {
+    const size_t fast_a = base + sizeof(double) * (size_t)b * (b | 1);       // A only; eigenvectors in global memory
+    if ((fast <= cap || fast_a <= cap) && !generic_only) {
         static bool attr_fast = false;
         if (!attr_fast) {
-            GEMB_CUDA(cudaFuncSetAttribute(eigh_jacobi_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+            GEMB_CUDA(cudaFuncSetAttribute(eigh_jacobi_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+            GEMB_CUDA(cudaFuncSetAttribute(eigh_jacobi_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
             attr_fast = true;
         }
-        eigh_jacobi_fast_kernel<<<1, 1024, fast, ctx->stream>>>(b, G, w, Z, 30, rel_tol);
+        if (fast <= cap) eigh_jacobi_fast_kernel<false><<<1, 1024, fast, ctx->stream>>>(b, G, w, Z, Zscratch, 30, rel_tol);
+        else eigh_jacobi_fast_kernel<true><<<1, 1024, fast_a, ctx->stream>>>(b, G, w, Z, Zscratch, 30, rel_tol);
         GEMB_CUDA(cudaGetLastError());
         count_launch();
         return GEMB_OK;

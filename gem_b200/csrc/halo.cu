@@ -156,7 +156,7 @@ int halo_build(gemb_graph *g) {
     GEMB_ARG(n_H < ((int64_t)1 << 29), "halo too large for 29-bit slots");
 
     // ---- remapped column ids
-    GEMB_CUDA(dmalloc(&H.indices_ext, sizeof(int32_t) * std::max<int64_t>(nnz, 1)));
+    GEMB_CUDA(dmalloc(&H.indices_ext, sizeof(int32_t) * (std::max<int64_t>(nnz, 1) + 4)));   // + the x4 padding the bulk copies of spmm.cu read
     if (nnz > 0) {
         halo_remap_kernel<<<c->sm_count * 8, 256, 0, st>>>(nnz, g->A.indices, lo, hi, Hd, n_H, (int32_t)g->n_shard, H.indices_ext);
         GEMB_CUDA(cudaGetLastError());

@@ -1289,12 +1289,27 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
 
     double nrm = 0.0, hard_bound = 0.0;
     int J = o.katz_terms;
-    bool need_power = (J <= 0 && algo == 1);
+    bool have_nrm = false;
+    if (beta < 0.f) {
+        // beta given relative to the spectral radius: beta = |beta| / ||A||_2 (= rho(A) for the symmetric graphs of
+        // BASELINE.json configs[3]: "beta = 0.5 / rho_hat"), ||A||_2 by power iteration on a width-4 block
+        GEMB_TRY(estimate_norm2(W, o.seed, W.buf[3], W.buf[4], W.buf[2], &nrm));
+        if (!(nrm > 0.0)) { set_error("beta < 0 asks for beta = |beta| / ||A||_2, but ||A||_2 = 0 (empty graph)"); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return GEMB_ERR_ARG; }
+        beta = (float)(-(double)beta / nrm);
+        have_nrm = true;
+        for (int i = 2; i < 5; i++) GEMB_CUDA(cudaMemsetAsync(W.buf[i], 0, blk, c->stream));
+    }
+    bool need_power = (J <= 0 && algo == 1) && !have_nrm;
     if (algo >= 2) {
         bool nonneg = false;
         GEMB_TRY(rowsum_bound(W, &hard_bound, &nonneg));
         if (nonneg && (double)beta * hard_bound * 1.02 < 1.0) nrm = -1.0;   // spectrum bounds from Ritz values
-        else need_power = true;
+        else need_power = !have_nrm;
+    }
+    if (have_nrm && nrm >= 0.0) {
+        if ((double)beta * nrm * 1.02 >= 1.0) { set_error("|beta| / ||A||_2 with |beta| >= 0.98: outside the Katz convergence radius"); cudaEventDestroy(ev0); cudaEventDestroy(ev1); return GEMB_ERR_DIVERGE; }
+        if (J <= 0) J = katz_terms_for(beta, nrm, o.katz_tol);
+        if (hard_bound <= 0.0) hard_bound = nrm;
     }
     if (need_power) {
         GEMB_TRY(estimate_norm2(W, o.seed, W.buf[3], W.buf[4], W.buf[2], &nrm));
@@ -1384,6 +1399,7 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         stats->h2d_ms = 0.0;
         stats->d2h_ms = d2h_ms;
         stats->norm2_A = (float)(nrm >= 0.0 ? nrm : hard_bound);   /* ||A||_inf when no power iteration ran */
+        stats->beta_used = beta;
         stats->ritz_change = (float)R.change;
         stats->resid_max = R.resid_max;
     }

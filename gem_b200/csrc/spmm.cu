@@ -187,117 +187,105 @@ spmm_heavy_finish_kernel(int n_heavy, const int32_t *__restrict__ heavy_row, con
     }
 }
 
-// ---- v3 (sm_100a): persistent CTAs walk row TILES; the tile's slice of the column-id (and value) arrays -- one
-// contiguous range of the CSR, rows being consecutive -- is staged into shared memory by ONE TMA bulk copy
-// (cp.async.bulk + mbarrier complete_tx) while the previous tile is still being gathered (2-slot ring).  The row
-// groups then read their column ids from shared memory: the dependent chain per row drops from
-// indptr -> indices -> X (three global round trips) to indptr -> X, and the ~nnz/4 broadcast LDGs of v1 (one L1
-// wavefront each) leave the L1 data pipe to the gathers.  Streaming operands (Xself, X0, Y) bypass L1 / are marked
-// evict-first so that L2 keeps X rows instead.  A tile whose slice exceeds the staging slot (hubs) reads its ids from
-// global memory as v1 does; rows above SPMM_HEAVY_DEG still go to the chunk kernels.
-constexpr int BULK_CAP = 2040;                 // staged ids per slot (+ up to 3 of alignment slack + 4 of over-read)
-template <bool HAS_VAL, bool HAS_PUSH>
+// ---- v3 (sm_100a): one CTA per row TILE (passes * rows_per_cta consecutive rows); the tile's slice of the column-id
+// (and value) arrays -- one contiguous range of the CSR -- is staged into shared memory by ONE TMA bulk copy
+// (cp.async.bulk + mbarrier complete_tx) issued by thread 0 while every row group fetches its row offsets; the other
+// resident CTAs of the SM hide the copy's latency.  The row groups then read their column ids from shared memory: the
+// dependent chain per row drops from indptr -> indices -> X (three global round trips) to indptr -> X, and the
+// ~nnz/4 broadcast LDGs of v1 (one L1 wavefront each) leave the L1 data pipe to the gathers.  Measured in
+// scripts/spmm_lab.cu (profiles/r02_spmm_lab.md): on par with v1 at 4 passes; the persistent 2-slot ring this replaced
+// lost 4 % to the per-tile CTA barrier, and evict-first hints on the streaming operands changed nothing.  A tile whose
+// slice exceeds the staging buffer (hubs) reads its ids from global memory as v1 does; rows above SPMM_HEAVY_DEG still go
+// to the chunk kernels.
+constexpr int BULK_CAP = 3072;                 // staged ids per tile (+ up to 3 of alignment slack + 4 of over-read)
+template <bool HAS_VAL, bool HAS_PUSH, bool HAS_X0, bool HAS_SELF>
 __global__ void __launch_bounds__(256)
 spmm_bulk_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                  const float *__restrict__ vals, int64_t n_rows, int64_t nnz, int G, int rows_per_cta, int tile_rows,
-                 int64_t n_tiles, float alpha, float gamma, float delta, const float4 *__restrict__ X,
+                 float alpha, float gamma, float delta, const float4 *__restrict__ X,
                  const float4 *__restrict__ Xself, const float4 *__restrict__ X0, float4 *__restrict__ Y,
                  int heavy_deg, HaloPushArgs P) {
-    __shared__ __align__(16) int32_t s_idx[2][BULK_CAP + 8];
-    __shared__ __align__(16) float s_val[HAS_VAL ? 2 : 1][HAS_VAL ? BULK_CAP + 8 : 4];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ int s_base[2];                  // first staged nonzero of the slot's tile, or -1: not staged
+    __shared__ __align__(16) int32_t s_idx[BULK_CAP + 8];
+    __shared__ __align__(16) float s_val[HAS_VAL ? BULK_CAP + 8 : 4];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_base;                     // first staged nonzero of the tile, or -1: not staged
     const int tid = threadIdx.x;
     const int lr = tid / G;
     const int c = tid - lr * G;
-    const bool active = lr < rows_per_cta;
-    const float4 *Xc = X + c;
-
-    // thread 0: stage tile `t` into slot `slot`
-    auto issue = [&](int64_t t, int slot) {
-        const int64_t r0 = t * tile_rows;
-        const int64_t r1 = r0 + tile_rows < n_rows ? r0 + tile_rows : n_rows;
+    const int64_t r0 = (int64_t)blockIdx.x * tile_rows;
+    const int64_t r1 = r0 + tile_rows < n_rows ? r0 + tile_rows : n_rows;
+    const uint32_t bar = tc::smem_u32(&s_bar);
+    if (tid == 0) {
+        tc::mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const int s = __ldg(indptr + r0), e = __ldg(indptr + r1);
         const int a0 = s & ~3;                                   // 16-byte aligned source
         int cnt = (e - a0 + 3) & ~3;
         if ((int64_t)a0 + cnt > ((nnz + 3) & ~(int64_t)3)) cnt = (int)(((nnz + 3) & ~(int64_t)3) - a0);   // arrays are padded to x4
-        const uint32_t bar = tc::smem_u32(&s_bar[slot]);
         if (e > s && cnt <= BULK_CAP + 4) {
-            s_base[slot] = a0;
+            s_base = a0;
             const uint32_t bytes = (uint32_t)cnt * 4u;
             tc::mbar_expect_tx(bar, HAS_VAL ? 2 * bytes : bytes);
-            tc::bulk_g2s(tc::smem_u32(&s_idx[slot][0]), indices + a0, bytes, bar);
-            if (HAS_VAL) tc::bulk_g2s(tc::smem_u32(&s_val[HAS_VAL ? slot : 0][0]), vals + a0, bytes, bar);
+            tc::bulk_g2s(tc::smem_u32(&s_idx[0]), indices + a0, bytes, bar);
+            if (HAS_VAL) tc::bulk_g2s(tc::smem_u32(&s_val[0]), vals + a0, bytes, bar);
         } else {
-            s_base[slot] = -1;
-            tc::mbar_arrive(bar);                                // keep the phase sequence: an empty transaction
+            s_base = -1;
+            tc::mbar_arrive(bar);                                // an empty transaction completes the phase
         }
-    };
-
-    if (tid == 0) {
-        tc::mbar_init(tc::smem_u32(&s_bar[0]), 1);
-        tc::mbar_init(tc::smem_u32(&s_bar[1]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if ((int64_t)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
     }
     __syncthreads();
-    int it = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
-        const int slot = it & 1;
-        if (tid == 0 && t + gridDim.x < n_tiles) issue(t + gridDim.x, slot ^ 1);   // slot^1 was released by the barrier below
-        tc::mbar_wait(tc::smem_u32(&s_bar[slot]), (uint32_t)(it >> 1) & 1);
-        const int base = s_base[slot];
-        const int32_t *sidx = &s_idx[slot][0];
-        const float *sval = &s_val[HAS_VAL ? slot : 0][0];
-        const int64_t r0 = t * tile_rows;
-        const int64_t r1 = r0 + tile_rows < n_rows ? r0 + tile_rows : n_rows;
-        if (active) {
-            for (int64_t row = r0 + lr; row < r1; row += rows_per_cta) {
-                const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
-                if (heavy_deg > 0 && e - s > heavy_deg) continue;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                int i = s;
-                if (base >= 0) {
-                    const int32_t *li = sidx - base;
-                    const float *lv = sval - base;
-                    for (; i + 4 <= e; i += 4) {
-                        const int c0 = li[i], c1 = li[i + 1], c2 = li[i + 2], c3 = li[i + 3];
-                        const float4 x0 = __ldg(Xc + (int64_t)c0 * G), x1 = __ldg(Xc + (int64_t)c1 * G);
-                        const float4 x2 = __ldg(Xc + (int64_t)c2 * G), x3 = __ldg(Xc + (int64_t)c3 * G);
-                        fma4(acc, HAS_VAL ? lv[i] : 1.f, x0); fma4(acc, HAS_VAL ? lv[i + 1] : 1.f, x1);
-                        fma4(acc, HAS_VAL ? lv[i + 2] : 1.f, x2); fma4(acc, HAS_VAL ? lv[i + 3] : 1.f, x3);
-                    }
-                    for (; i < e; i++) fma4(acc, HAS_VAL ? lv[i] : 1.f, __ldg(Xc + (int64_t)li[i] * G));
-                } else {
-                    for (; i + 4 <= e; i += 4) {
-                        const int c0 = __ldg(indices + i), c1 = __ldg(indices + i + 1);
-                        const int c2 = __ldg(indices + i + 2), c3 = __ldg(indices + i + 3);
-                        const float4 x0 = __ldg(Xc + (int64_t)c0 * G), x1 = __ldg(Xc + (int64_t)c1 * G);
-                        const float4 x2 = __ldg(Xc + (int64_t)c2 * G), x3 = __ldg(Xc + (int64_t)c3 * G);
-                        fma4(acc, HAS_VAL ? __ldg(vals + i) : 1.f, x0); fma4(acc, HAS_VAL ? __ldg(vals + i + 1) : 1.f, x1);
-                        fma4(acc, HAS_VAL ? __ldg(vals + i + 2) : 1.f, x2); fma4(acc, HAS_VAL ? __ldg(vals + i + 3) : 1.f, x3);
-                    }
-                    for (; i < e; i++) fma4(acc, HAS_VAL ? __ldg(vals + i) : 1.f, __ldg(Xc + (int64_t)__ldg(indices + i) * G));
+    if (lr >= rows_per_cta) return;
+    int64_t row = r0 + lr;
+    int s = 0, e = 0;
+    if (row < r1) { s = __ldg(indptr + row); e = __ldg(indptr + row + 1); }     // in flight together with the bulk copy
+    tc::mbar_wait(bar, 0);
+    const int base = s_base;
+    const int32_t *li = s_idx - base;
+    const float *lv = s_val - base;
+    const float4 *Xc = X + c;
+    for (; row < r1; row += rows_per_cta) {
+        if (!(heavy_deg > 0 && e - s > heavy_deg)) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            int i = s;
+            if (base >= 0) {
+                for (; i + 4 <= e; i += 4) {
+                    const int c0 = li[i], c1 = li[i + 1], c2 = li[i + 2], c3 = li[i + 3];
+                    const float4 x0 = __ldg(Xc + (int64_t)c0 * G), x1 = __ldg(Xc + (int64_t)c1 * G);
+                    const float4 x2 = __ldg(Xc + (int64_t)c2 * G), x3 = __ldg(Xc + (int64_t)c3 * G);
+                    fma4(acc, HAS_VAL ? lv[i] : 1.f, x0); fma4(acc, HAS_VAL ? lv[i + 1] : 1.f, x1);
+                    fma4(acc, HAS_VAL ? lv[i + 2] : 1.f, x2); fma4(acc, HAS_VAL ? lv[i + 3] : 1.f, x3);
                 }
-                float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
-                if (Xself) {
-                    const float4 z = __ldcs(Xself + row * G + c);
-                    r.x = fmaf(gamma, z.x, r.x); r.y = fmaf(gamma, z.y, r.y); r.z = fmaf(gamma, z.z, r.z); r.w = fmaf(gamma, z.w, r.w);
+                for (; i < e; i++) fma4(acc, HAS_VAL ? lv[i] : 1.f, __ldg(Xc + (int64_t)li[i] * G));
+            } else {
+                for (; i + 4 <= e; i += 4) {
+                    const int c0 = __ldg(indices + i), c1 = __ldg(indices + i + 1);
+                    const int c2 = __ldg(indices + i + 2), c3 = __ldg(indices + i + 3);
+                    const float4 x0 = __ldg(Xc + (int64_t)c0 * G), x1 = __ldg(Xc + (int64_t)c1 * G);
+                    const float4 x2 = __ldg(Xc + (int64_t)c2 * G), x3 = __ldg(Xc + (int64_t)c3 * G);
+                    fma4(acc, HAS_VAL ? __ldg(vals + i) : 1.f, x0); fma4(acc, HAS_VAL ? __ldg(vals + i + 1) : 1.f, x1);
+                    fma4(acc, HAS_VAL ? __ldg(vals + i + 2) : 1.f, x2); fma4(acc, HAS_VAL ? __ldg(vals + i + 3) : 1.f, x3);
                 }
-                if (X0) {
-                    const float4 z = __ldcs(X0 + row * G + c);
-                    r.x = fmaf(delta, z.x, r.x); r.y = fmaf(delta, z.y, r.y); r.z = fmaf(delta, z.z, r.z); r.w = fmaf(delta, z.w, r.w);
-                }
-                __stcs(Y + row * G + c, r);
-                if (HAS_PUSH) {
-                    for (int i2 = P.push_ptr[row], e2 = P.push_ptr[row + 1]; i2 < e2; i2++) {
-                        const uint32_t d = P.push_dst[i2];
-                        P.peer[d >> 29][(P.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + c] = r;
-                    }
+                for (; i < e; i++) fma4(acc, HAS_VAL ? __ldg(vals + i) : 1.f, __ldg(Xc + (int64_t)__ldg(indices + i) * G));
+            }
+            float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+            if (HAS_SELF) {
+                const float4 z = __ldg(Xself + row * G + c);
+                r.x = fmaf(gamma, z.x, r.x); r.y = fmaf(gamma, z.y, r.y); r.z = fmaf(gamma, z.z, r.z); r.w = fmaf(gamma, z.w, r.w);
+            }
+            if (HAS_X0) {
+                const float4 z = __ldg(X0 + row * G + c);
+                r.x = fmaf(delta, z.x, r.x); r.y = fmaf(delta, z.y, r.y); r.z = fmaf(delta, z.z, r.z); r.w = fmaf(delta, z.w, r.w);
+            }
+            Y[row * G + c] = r;
+            if (HAS_PUSH) {
+                for (int i2 = P.push_ptr[row], e2 = P.push_ptr[row + 1]; i2 < e2; i2++) {
+                    const uint32_t d = P.push_dst[i2];
+                    P.peer[d >> 29][(P.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + c] = r;
                 }
             }
         }
-        __syncthreads();     // every group is done with this slot before it is refilled two tiles later
+        const int64_t nrow = row + rows_per_cta;
+        if (nrow < r1) { s = __ldg(indptr + nrow); e = __ldg(indptr + nrow + 1); }
     }
 }
 
@@ -308,15 +296,9 @@ static int spmm_variant() {   // GEMB_SPMM=v1 selects the round-1 kernel (A/B ru
 }
 static int spmm_tile_passes() {   // rows per tile = passes * (256 / G)
     static int t = -1;
-    if (t < 0) { const char *e = getenv("GEMB_SPMM_PASSES"); t = e ? atoi(e) : 4; if (t < 1) t = 1; if (t > 64) t = 64; }
+    if (t < 0) { const char *e = getenv("GEMB_SPMM_PASSES"); t = e ? atoi(e) : 4; if (t < 1) t = 1; if (t > 16) t = 16; }
     return t;
 }
-static int spmm_ctas_per_sm() {
-    static int t = -1;
-    if (t < 0) { const char *e = getenv("GEMB_SPMM_CTAS"); t = e ? atoi(e) : 8; if (t < 1) t = 1; if (t > 8) t = 8; }
-    return t;
-}
-
 int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha,
                 const float *X, const float *X0, float *Y) {
     return spmm3_launch(ctx, A, n_rows, b, alpha, X, 0.f, nullptr, 1.f, X0, Y, nullptr);
@@ -331,7 +313,7 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
     if (spmm_variant() == 3 && G <= 256 && n_rows >= 4096) {
         const int tile_rows = rows_per_cta * spmm_tile_passes();
         const int64_t n_tiles = (n_rows + tile_rows - 1) / tile_rows;
-        const int grid3 = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * spmm_ctas_per_sm());
+        GEMB_ARG(n_tiles < (int64_t)2147483647, "grid too large");
         const bool heavy3 = A.n_items > 0;
         const int hd = heavy3 ? SPMM_HEAVY_DEG : 0;
         HaloPushArgs PA3;
@@ -339,11 +321,17 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
         if (push) PA3 = *push;
         const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0, *XS4 = (const float4 *)Xself;
         float4 *Y4 = (float4 *)Y;
-#define LAUNCH3(V, PU)                                                                                                   \
-        spmm_bulk_kernel<V, PU><<<grid3, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, A.nnz, G, rows_per_cta, \
-                                                                tile_rows, n_tiles, alpha, gamma, delta, X4, XS4, X04, Y4, hd, PA3)
-        if (A.data) { if (push) LAUNCH3(true, true); else LAUNCH3(true, false); }
-        else { if (push) LAUNCH3(false, true); else LAUNCH3(false, false); }
+#define LAUNCH3(V, PU, Z, S)                                                                                             \
+        spmm_bulk_kernel<V, PU, Z, S><<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, A.nnz, G, rows_per_cta, \
+                                                                                  tile_rows, alpha, gamma, delta, X4, XS4, X04, Y4, hd, PA3)
+#define LAUNCH3B(V, PU)                                                                                                  \
+        do {                                                                                                             \
+            if (X0 && Xself) LAUNCH3(V, PU, true, true); else if (X0) LAUNCH3(V, PU, true, false);                       \
+            else if (Xself) LAUNCH3(V, PU, false, true); else LAUNCH3(V, PU, false, false);                              \
+        } while (0)
+        if (A.data) { if (push) LAUNCH3B(true, true); else LAUNCH3B(true, false); }
+        else { if (push) LAUNCH3B(false, true); else LAUNCH3B(false, false); }
+#undef LAUNCH3B
 #undef LAUNCH3
         GEMB_CUDA(cudaGetLastError());
         count_launch();

@@ -117,7 +117,12 @@ class HOPE(StaticGraphEmbedding):
                 g = _native.DeviceGraph(ctx, csr.n, csr.indptr, csr.indices, csr.data_f32(),
                                         t.indptr, t.indices, t.data_f32())
             try:
-                X, sigma, st = g.hope(int(self._d), float(self._beta), out=out, **opts)
+                # beta_over_rho=c (extra hyper-parameter): beta = c / rho_hat(A), estimated on the device (BASELINE configs[3])
+                bor = getattr(self, '_beta_over_rho', None)
+                beta_arg = float(self._beta) if bor is None else -float(bor)
+                X, sigma, st = g.hope(int(self._d), beta_arg, out=out, **opts)
+                if bor is not None:
+                    self._beta = float(st['beta_used'])
                 self._svd_error = None
                 want_err = getattr(self, '_svd_error_probes', None)
                 if world == 1 and (csr.n <= 4096 if want_err is None else want_err is not False):

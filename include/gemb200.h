@@ -61,6 +61,16 @@ int gemb_host_free(void *p);
 int gemb_mem_trim(void);
 size_t gemb_mem_cached_bytes(void);
 
+/* ---- bench infrastructure: Graph500 R-MAT generator on the device (BASELINE.json configs[3], configs[4]: scale 24).
+ * No reference counterpart (GEM ships no generator; gem/tests load fixed fixtures); the host generator
+ * gem_b200/synth.py::rmat makes the same kind of graph with NumPy for the small parity cases.
+ * Rows [row0, row0 + n_rows) (n_rows < 0: all) of the symmetrised, loop-free, duplicate-free graph with sorted column
+ * ids.  indices_out = NULL: only *nnz_out (shard) and *nnz_total_out (graph) are set; otherwise indptr_out (n_rows + 1
+ * int64, shard-local offsets) and indices_out (cap >= nnz) are filled.  Counter-based RNG: identical on every rank. */
+int gemb_synth_rmat(gemb_ctx *ctx, int scale, int edge_factor, double a, double b, double c, uint64_t seed, int permute,
+                    int64_t row0, int64_t n_rows, int64_t *nnz_out, int64_t *nnz_total_out, int64_t *indptr_out,
+                    int32_t *indices_out, int64_t cap);
+
 /* ---- multi-GPU: one process per GPU; rank 0 makes the id, every rank calls init.
  * (No reference counterpart: GEM is single-process) */
 #define GEMB_UNIQUE_ID_BYTES 128
@@ -158,10 +168,13 @@ typedef struct {
     int64_t halo_rows;     /* mg_mode 2: distinct remote rows this shard references */
     int64_t push_rows;     /* mg_mode 2: (row, peer) pairs this rank stores per exchanged block */
     int64_t pushes;        /* mg_mode 2: blocks exchanged in this call (NVLink bytes out = pushes*push_rows*4*block) */
+    float beta_used;       /* the beta the solve ran with (differs from the argument when that was negative) */
 } gemb_hope_stats;
 
 /* X_out: n_local x d host buffer, or NULL to leave the result on the device (bench `value`).
- * sigma_out: d/2 floats (ascending) or NULL. */
+ * sigma_out: d/2 floats (ascending) or NULL.
+ * beta > 0: hope.py's beta.  beta < 0: beta = |beta| / ||A||_2, ||A||_2 (= rho(A) for symmetric A) estimated by power
+ * iteration inside the call -- BASELINE.json configs[3] prescribes beta = 0.5 / rho_hat(A); stats->beta_used reports it. */
 int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts *opts, float *X_out,
               float *sigma_out, gemb_hope_stats *stats);
 

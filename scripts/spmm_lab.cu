@@ -128,7 +128,7 @@ __device__ __forceinline__ float4 ldg_na(const float4 *p) {   // read-only path,
 }
 
 // ---- rm variants: UNROLL gathers in flight, NA = gathers bypass L1 allocation
-template <int UNROLL, bool NA>
+template <int UNROLL, int HINT>
 __global__ void __launch_bounds__(256)
 rowgroup_u_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, int64_t n, int G, int rpc,
                   float alpha, float gamma, float delta, const float4 *__restrict__ X, const float4 *__restrict__ X0,
@@ -147,25 +147,25 @@ rowgroup_u_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict_
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) cc[u] = __ldg(indices + i + u);
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) x[u] = NA ? ldg_na(Xc + (int64_t)cc[u] * G) : __ldg(Xc + (int64_t)cc[u] * G);
+        for (int u = 0; u < UNROLL; u++) x[u] = (HINT & 4) ? ldg_na(Xc + (int64_t)cc[u] * G) : __ldg(Xc + (int64_t)cc[u] * G);
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) fma4(acc, x[u]);
     }
-    for (; i < e; i++) fma4(acc, NA ? ldg_na(Xc + (int64_t)__ldg(indices + i) * G) : __ldg(Xc + (int64_t)__ldg(indices + i) * G));
+    for (; i < e; i++) fma4(acc, (HINT & 4) ? ldg_na(Xc + (int64_t)__ldg(indices + i) * G) : __ldg(Xc + (int64_t)__ldg(indices + i) * G));
     const float4 xs = __ldg(Xc + row * G);
-    const float4 z = __ldcs(X0 + row * G + c);
+    const float4 z = (HINT & 1) ? __ldcs(X0 + row * G + c) : __ldg(X0 + row * G + c);
     float4 r;
     r.x = alpha * acc.x + gamma * xs.x + delta * z.x;
     r.y = alpha * acc.y + gamma * xs.y + delta * z.y;
     r.z = alpha * acc.z + gamma * xs.z + delta * z.z;
     r.w = alpha * acc.w + gamma * xs.w + delta * z.w;
-    __stcs(Y + row * G + c, r);
+    if (HINT & 2) __stcs(Y + row * G + c, r); else Y[row * G + c] = r;
 }
 
 // ---- rm + the CTA's slice of the column ids staged into shared memory by ONE TMA bulk copy (non-persistent: one tile
 // of PASSES * rpc consecutive rows per CTA; the other resident CTAs of the SM hide the copy's latency)
 constexpr int TMA_CAP = 3072;
-template <int UNROLL>
+template <int UNROLL, int HINT>
 __global__ void __launch_bounds__(256)
 rowgroup_tma_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, int64_t n, int64_t nnz_pad, int G, int rpc,
                     int passes, float alpha, float gamma, float delta, const float4 *__restrict__ X,
@@ -226,13 +226,13 @@ rowgroup_tma_kernel(const int32_t *__restrict__ indptr, const int32_t *__restric
         }
         for (; i < e; i++) fma4(acc, __ldg(Xc + (int64_t)(li ? li[i] : __ldg(indices + i)) * G));
         const float4 xs = __ldg(Xc + row * G);
-        const float4 z = __ldcs(X0 + row * G + c);
+        const float4 z = (HINT & 1) ? __ldcs(X0 + row * G + c) : __ldg(X0 + row * G + c);
         float4 r;
         r.x = alpha * acc.x + gamma * xs.x + delta * z.x;
         r.y = alpha * acc.y + gamma * xs.y + delta * z.y;
         r.z = alpha * acc.z + gamma * xs.z + delta * z.z;
         r.w = alpha * acc.w + gamma * xs.w + delta * z.w;
-        __stcs(Y + row * G + c, r);
+        if (HINT & 2) __stcs(Y + row * G + c, r); else Y[row * G + c] = r;
         const int64_t nrow = row + rpc;
         if (nrow < r1) { s = __ldg(indptr + nrow); e = __ldg(indptr + nrow + 1); }
     }
@@ -313,13 +313,14 @@ int main(int argc, char **argv) {
                 printf("{\"variant\": \"%s\", \"b\": %d, \"param\": %d, \"ms_per_sweep\": %.4f, \"maxdiff\": %.3g}\n", name, b, extra, ms / reps, md);
                 fflush(stdout);
             };
-#define RMU(U, NA) timeit(NA ? "rm_na" : "rm_u", U, [&]() { rowgroup_u_kernel<U, NA><<<grid, 256>>>(d_ip, d_ix, n, G, rpc, alpha, gamma, delta, (const float4 *)X, (const float4 *)X0, (float4 *)Y); });
-            RMU(4, false) RMU(8, false) RMU(4, true) RMU(8, true)
+#define RMU(U, H) timeit("rm_u" #U "_h" #H, H, [&]() { rowgroup_u_kernel<U, H><<<grid, 256>>>(d_ip, d_ix, n, G, rpc, alpha, gamma, delta, (const float4 *)X, (const float4 *)X0, (float4 *)Y); });
+            RMU(4, 0) RMU(4, 1) RMU(4, 2) RMU(4, 3) RMU(8, 0) RMU(2, 0)
 #undef RMU
-            for (int passes : {1, 2, 4, 8}) {
+            for (int passes : {2, 3, 4, 6}) {
                 const unsigned g2 = (unsigned)((n + (int64_t)rpc * passes - 1) / ((int64_t)rpc * passes));
-                timeit("rm_tma_u4", passes, [&]() { rowgroup_tma_kernel<4><<<g2, 256>>>(d_ip, d_ix, n, nnz_pad, G, rpc, passes, alpha, gamma, delta, (const float4 *)X, (const float4 *)X0, (float4 *)Y); });
-                timeit("rm_tma_u8", passes, [&]() { rowgroup_tma_kernel<8><<<g2, 256>>>(d_ip, d_ix, n, nnz_pad, G, rpc, passes, alpha, gamma, delta, (const float4 *)X, (const float4 *)X0, (float4 *)Y); });
+                timeit("rm_tma_u4_h0", passes, [&]() { rowgroup_tma_kernel<4, 0><<<g2, 256>>>(d_ip, d_ix, n, nnz_pad, G, rpc, passes, alpha, gamma, delta, (const float4 *)X, (const float4 *)X0, (float4 *)Y); });
+                timeit("rm_tma_u2_h0", passes, [&]() { rowgroup_tma_kernel<2, 0><<<g2, 256>>>(d_ip, d_ix, n, nnz_pad, G, rpc, passes, alpha, gamma, delta, (const float4 *)X, (const float4 *)X0, (float4 *)Y); });
+                timeit("rm_tma_u4_h1", passes, [&]() { rowgroup_tma_kernel<4, 1><<<g2, 256>>>(d_ip, d_ix, n, nnz_pad, G, rpc, passes, alpha, gamma, delta, (const float4 *)X, (const float4 *)X0, (float4 *)Y); });
             }
         }
         if (quick) { CK(cudaFree(X)); CK(cudaFree(X0)); CK(cudaFree(Y)); CK(cudaFree(Yref)); continue; }
