@@ -146,16 +146,18 @@ __global__ void __launch_bounds__(288, 1) apply_tc_kernel(ApplyTcParams p) {
                         tc::bulk_wait_read_all();                                         // staging slot may be overwritten
                         tc::mbar_arrive(tc::smem_u32(&s_slot_free[slot]));
                     }
-                } else if (warp == 0) {
-                    // strided output (the two halves of X = [U sqrt(S) | V sqrt(S)], ldo = d): one bulk store per row,
-                    // four rows per lane of warp 0
-                    const int vr = tile_rows(t);
+                } else {
+                    // strided output (the two halves of X = [U sqrt(S) | V sqrt(S)], ldo = d): the four epilogue warps copy
+                    // the staged tile with coalesced 16-byte stores (128 per-row bulk stores measured 0.43 ms per launch
+                    // against 0.22 ms for the contiguous form)
+                    const int vr = tile_rows(t), q4 = p.b2 >> 2;
                     float *orow = p.Out + tile_row0(t) * p.ldo;
-                    for (int r = lane; r < vr; r += 32)
-                        tc::bulk_s2g(orow + (size_t)r * p.ldo, tc::smem_u32(stage + (size_t)r * p.b2 * 4), (uint32_t)p.b2 * 4u);
-                    tc::bulk_wait_read_all();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(tc::smem_u32(&s_slot_free[slot]));
+                    for (int idx = tid; idx < vr * q4; idx += 128) {
+                        const int r = idx / q4, c4 = idx - r * q4;
+                        *(float4 *)(orow + (size_t)r * p.ldo + 4 * c4) = *(const float4 *)(stage + ((size_t)r * p.b2 + 4 * c4) * 4);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (tid == 0) tc::mbar_arrive(tc::smem_u32(&s_slot_free[slot]));
                 }
             }
         };

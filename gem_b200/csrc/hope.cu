@@ -999,7 +999,7 @@ static int hope_lanczos(HopeWork &W, const Opts &o, int d, float beta, double ha
         for (int r = 0; r < m; r++) for (int q = 0; q < m; q++) Tm[(size_t)r * m + q] = T[(size_t)r * mt + q];
         GEMB_CUDA(cudaMemcpyAsync(Td, Tm.data(), sizeof(double) * m * m, cudaMemcpyHostToDevice, c->stream));
         GEMB_TRY(c->t_dense.begin(c->stream));
-        GEMB_TRY(eigh_launch(c, m, Td, wd, Yd, Zs, 1e-12));
+        GEMB_TRY(eigh_launch(c, m, Td, wd, Yd, Zs, 1e-9));      // Ritz values are needed to ~1e-6, the vectors feed fp32 GEMMs
         GEMB_TRY(c->t_dense.end(c->stream));
         GEMB_CUDA(cudaMemcpyAsync(theta.data(), wd, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
         GEMB_CUDA(cudaMemcpyAsync(Y.data(), Yd, sizeof(double) * m * m, cudaMemcpyDeviceToHost, c->stream));
