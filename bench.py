@@ -572,7 +572,9 @@ def run_hope(args, dist, rank, world, local):
     if rank == 0:
         mg = {0: 'single GPU', 1: 'row-sharded CSR x%d, ncclAllGather of the block per SpMM' % world,
               2: 'row-sharded CSR x%d; needed rows only, stored into the peers\' halo slots over NVLink (CUDA IPC) by the '
-                 'producing kernel; b x b Gram all-reduce on NCCL' % world}[stats.get('mg_mode', 0)]
+                 'producing kernel; b x b Gram all-reduce on NCCL' % world}
+        mg[3] = mg[2] + '; halo copies travel as fp16'
+        mg = mg[stats.get('mg_mode', 0)]
         line = {'metric': 'nodes/sec embedded at d=128', 'value': value, 'unit': 'nodes/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
                 'higher_is_better': True, 'scaling': 'strong' if rmat else 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -591,7 +593,8 @@ def run_hope(args, dist, rank, world, local):
                            'parallelism': mg,
                            'exchange': None if world == 1 else {'halo_rows_rank0': stats.get('halo_rows'), 'push_rows_rank0': stats.get('push_rows'),
                                                                 'blocks_exchanged_per_step': stats.get('pushes', 0) / args.steps,
-                                                                'nvlink_bytes_out_per_step_rank0': stats.get('pushes', 0) / args.steps * stats.get('push_rows', 0) * 4 * stats['block']},
+                                                                'nvlink_bytes_out_per_step_rank0': stats.get('push_bytes', 0.0) / args.steps,
+                                                                'wire': 'fp16 (x 2^12) for the filter / basis blocks, fp32 for the raw warm-up blocks' if stats.get('mg_mode') == 3 else 'fp32'},
                            'l2_policy': 'inputs larger than L2 (CSR %.0f MB + 5 blocks of %.0f MB vs 126 MB L2)' % (
                                (nnz_all * 4 + n_all * 4) / 1e6 / world, n_all * stats['block'] * 4 / 1e6 / world)},
                 'wall_ms_per_step': wall_s * 1e3 / args.steps, 'graph_gen_s': gen_s,

@@ -41,7 +41,7 @@ class HopeStats(ctypes.Structure):
                 ('d2h_ms', ctypes.c_double), ('norm2_A', ctypes.c_float), ('ritz_change', ctypes.c_float),
                 ('resid_max', ctypes.c_float), ('resid_est', ctypes.c_float), ('mg_mode', ctypes.c_int32),
                 ('halo_rows', ctypes.c_int64), ('push_rows', ctypes.c_int64), ('pushes', ctypes.c_int64),
-                ('beta_used', ctypes.c_float)]
+                ('beta_used', ctypes.c_float), ('push_bytes', ctypes.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != 'struct_size'}

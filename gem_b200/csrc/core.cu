@@ -218,6 +218,7 @@ int gemb_ctx_create(int device, gemb_ctx **out) {
 int gemb_ctx_destroy(gemb_ctx *c) {
     if (!c) return GEMB_OK;
     cudaSetDevice(c->device);
+    gemb::halo_pool_release(c);
     if (c->comm) {
         NcclApi *api = nccl_api();
         if (api) api->CommDestroy((ncclComm_t)c->comm);

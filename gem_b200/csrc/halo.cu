@@ -227,70 +227,100 @@ int halo_build(gemb_graph *g) {
     dfree(rem); dfree(rem_sorted); dfree(Hd); dfree(d_num); dfree(tmp); dfree(Hpad); dfree(Hall); dfree(seg_dev);
     dfree(cnt); dfree(stmp);
 
-    // ---- barrier flags (plain cudaMalloc: exported through CUDA IPC, never recycled by the block cache)
-    GEMB_CUDA(cudaMalloc(&H.flags, sizeof(unsigned long long) * GEMB_MAX_RANKS));
-    GEMB_CUDA(cudaMemset(H.flags, 0, sizeof(unsigned long long) * GEMB_MAX_RANKS));
-    GEMB_CUDA(cudaMalloc(&H.timeout_flag, sizeof(int)));
-    GEMB_CUDA(cudaMemset(H.timeout_flag, 0, sizeof(int)));
-    void *mine[1] = {H.flags};
-    void *peers[GEMB_MAX_RANKS] = {};
-    GEMB_TRY(ipc_exchange(c, mine, 1, peers));
-    for (int q = 0; q < P; q++) H.peer_flags[q] = (unsigned long long *)peers[q];
-    H.epoch = 0;
+    // ---- barrier flags: owned by the context (plain cudaMalloc: exported through CUDA IPC, never recycled by the block
+    //      cache), set up once and shared by every graph of this context
+    gemb_halo_pool &PL = c->halo_pool;
+    if (!PL.flags) {
+        GEMB_CUDA(cudaMalloc(&PL.flags, sizeof(unsigned long long) * GEMB_MAX_RANKS));
+        GEMB_CUDA(cudaMemset(PL.flags, 0, sizeof(unsigned long long) * GEMB_MAX_RANKS));
+        GEMB_CUDA(cudaMalloc(&PL.timeout_flag, sizeof(int)));
+        GEMB_CUDA(cudaMemset(PL.timeout_flag, 0, sizeof(int)));
+        void *mine[1] = {PL.flags};
+        void *peers[GEMB_MAX_RANKS] = {};
+        GEMB_TRY(ipc_exchange(c, mine, 1, peers));
+        for (int q = 0; q < P; q++) PL.peer_flags[q] = (unsigned long long *)peers[q];
+        PL.epoch = 0;
+    }
+    H.flags = PL.flags;
+    H.timeout_flag = PL.timeout_flag;
+    for (int q = 0; q < P; q++) H.peer_flags[q] = PL.peer_flags[q];
     H.ready = true;
     return GEMB_OK;
 }
 
-static int halo_release_buffers(gemb_graph *g) {
-    gemb_halo &H = g->halo;
-    gemb_ctx *c = g->ctx;
-    if (H.nbuf == 0) return GEMB_OK;
+// collective: every rank drops its mappings of the peers' blocks, then frees its own
+static int halo_pool_drop_blocks(gemb_ctx *c) {
+    gemb_halo_pool &PL = c->halo_pool;
+    if (PL.nbuf == 0) return GEMB_OK;
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < H.nbuf; i++)
+    for (int i = 0; i < PL.nbuf; i++)
         for (int q = 0; q < c->nranks; q++)
-            if (q != c->rank && H.peer_buf[i][q]) { cudaIpcCloseMemHandle(H.peer_buf[i][q]); H.peer_buf[i][q] = nullptr; }
+            if (q != c->rank && PL.peer_buf[i][q]) { cudaIpcCloseMemHandle(PL.peer_buf[i][q]); PL.peer_buf[i][q] = nullptr; }
     GEMB_TRY(nccl_barrier(c));     // nobody still maps what is freed next
-    for (int i = 0; i < H.nbuf; i++) { cudaFree(H.buf[i]); H.buf[i] = nullptr; }
-    H.nbuf = 0; H.width = 0;
+    for (int i = 0; i < PL.nbuf; i++) { cudaFree(PL.buf[i]); PL.buf[i] = nullptr; }
+    PL.nbuf = 0; PL.cap_floats = 0;
     return GEMB_OK;
 }
 
 int halo_buffers(gemb_graph *g, int nbuf, int width) {
     gemb_halo &H = g->halo;
     gemb_ctx *c = g->ctx;
+    gemb_halo_pool &PL = c->halo_pool;
+    NcclApi *api = nccl_api();
+    if (!api) return GEMB_ERR_NCCL;
     GEMB_ARG(H.ready && nbuf >= 1 && nbuf <= GEMB_HALO_BUFS, "halo_buffers");
     const size_t rows = (size_t)(g->n_shard + H.halo_rows);
-    if (H.nbuf >= nbuf && H.width == width) {
-        for (int i = 0; i < nbuf; i++) GEMB_CUDA(cudaMemsetAsync(H.buf[i], 0, sizeof(float) * rows * width, c->stream));
-        return GEMB_OK;
-    }
-    GEMB_TRY(halo_release_buffers(g));
-    void *mine[GEMB_HALO_BUFS];
-    for (int i = 0; i < nbuf; i++) {
-        cudaError_t e = cudaMalloc(&H.buf[i], sizeof(float) * std::max<size_t>(rows * width, 1));
-        if (e != cudaSuccess) {
-            (void)cudaGetLastError();
-            gemb_mem_trim();
-            e = cudaMalloc(&H.buf[i], sizeof(float) * std::max<size_t>(rows * width, 1));
+    // the pool is (re)built only when some rank needs more than it holds: the decision comes from an all-reduce (max)
+    // of the need, so every rank takes the same branch
+    long long need = (long long)(rows * (size_t)width), *d_need = nullptr;
+    GEMB_CUDA(dmalloc(&d_need, sizeof(long long)));
+    GEMB_CUDA(cudaMemcpyAsync(d_need, &need, sizeof need, cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(api->AllReduce(d_need, d_need, 1, ncclInt64, ncclMax, (ncclComm_t)c->comm, c->stream), "ncclAllReduce(halo block size)");
+    GEMB_CUDA(cudaMemcpyAsync(&need, d_need, sizeof need, cudaMemcpyDeviceToHost, c->stream));
+    GEMB_CUDA(cudaStreamSynchronize(c->stream));
+    dfree(d_need);
+    if (PL.nbuf < nbuf || PL.cap_floats < (size_t)need) {
+        GEMB_TRY(halo_pool_drop_blocks(c));
+        const size_t cap = (size_t)std::max<long long>(need, 1);
+        void *mine[GEMB_HALO_BUFS];
+        for (int i = 0; i < nbuf; i++) {
+            cudaError_t e = cudaMalloc(&PL.buf[i], sizeof(float) * cap);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                gemb_mem_trim();
+                e = cudaMalloc(&PL.buf[i], sizeof(float) * cap);
+            }
+            GEMB_CUDA(e);
+            mine[i] = PL.buf[i];
         }
-        GEMB_CUDA(e);
-        GEMB_CUDA(cudaMemsetAsync(H.buf[i], 0, sizeof(float) * rows * width, c->stream));
-        mine[i] = H.buf[i];
+        void *peers[GEMB_HALO_BUFS * GEMB_MAX_RANKS] = {};
+        PL.nbuf = nbuf; PL.cap_floats = cap;
+        GEMB_TRY(ipc_exchange(c, mine, nbuf, peers));
+        for (int i = 0; i < nbuf; i++)
+            for (int q = 0; q < c->nranks; q++) PL.peer_buf[i][q] = (float *)peers[(size_t)i * GEMB_MAX_RANKS + q];
+    } else {
+        // blocks of the previous call are being reused: no rank may still be pushing into them
+        GEMB_TRY(nccl_barrier(c));
     }
-    void *peers[GEMB_HALO_BUFS * GEMB_MAX_RANKS] = {};
+    for (int i = 0; i < nbuf; i++) {
+        GEMB_CUDA(cudaMemsetAsync(PL.buf[i], 0, sizeof(float) * rows * width, c->stream));
+        H.buf[i] = PL.buf[i];
+        for (int q = 0; q < c->nranks; q++) H.peer_buf[i][q] = PL.peer_buf[i][q];
+    }
     H.nbuf = nbuf; H.width = width;
-    GEMB_TRY(ipc_exchange(c, mine, nbuf, peers));
-    for (int i = 0; i < nbuf; i++)
-        for (int q = 0; q < c->nranks; q++) H.peer_buf[i][q] = (float *)peers[(size_t)i * GEMB_MAX_RANKS + q];
+    // the zero fill must be complete everywhere before any peer's first push can land
+    GEMB_CUDA(cudaStreamSynchronize(c->stream));
+    GEMB_TRY(nccl_barrier(c));
     return GEMB_OK;
 }
 
-void halo_push_args(const gemb_graph *g, int bi, HaloPushArgs *out) {
+void halo_push_args(const gemb_graph *g, int bi, HaloPushArgs *out, bool half) {
     const gemb_halo &H = g->halo;
     out->push_ptr = H.push_ptr;
     out->push_dst = H.push_dst;
     for (int q = 0; q < GEMB_MAX_RANKS; q++) out->peer[q] = (float4 *)H.peer_buf[bi][q];
     out->halo_row0 = g->n_shard;
+    out->half = half ? 1 : 0;
 }
 
 // group of G threads per local row: copy the row into every peer slot that references it
@@ -300,23 +330,18 @@ halo_push_kernel(int64_t n_rows, int G, int rows_per_cta, const float4 *__restri
     if (lr >= rows_per_cta) return;
     const int64_t row = (int64_t)blockIdx.x * rows_per_cta + lr;
     if (row >= n_rows) return;
-    const int s = P.push_ptr[row], e = P.push_ptr[row + 1];
-    if (s == e) return;
-    const float4 v = Y[row * G + c];
-    for (int i = s; i < e; i++) {
-        const uint32_t d = P.push_dst[i];
-        P.peer[d >> 29][(P.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + c] = v;
-    }
+    if (P.push_ptr[row] == P.push_ptr[row + 1]) return;
+    halo_push_row(P, row, G, c, Y[row * G + c]);
 }
 
-int halo_push_launch(gemb_graph *g, int bi, int width) {
+int halo_push_launch(gemb_graph *g, int bi, int width, bool half) {
     gemb_ctx *c = g->ctx;
     if (g->n_local == 0 || g->halo.push_total == 0) return GEMB_OK;
     const int G = width / 4;
     GEMB_ARG(G >= 1 && G <= 256, "width");
     const int rpc = 256 / G;
     HaloPushArgs P;
-    halo_push_args(g, bi, &P);
+    halo_push_args(g, bi, &P, half);
     halo_push_kernel<<<(unsigned)((g->n_local + rpc - 1) / rpc), 256, 0, c->stream>>>(g->n_local, G, rpc, (const float4 *)g->halo.buf[bi], P);
     GEMB_CUDA(cudaGetLastError());
     count_launch();
@@ -350,8 +375,8 @@ int halo_barrier(gemb_graph *g) {
     gemb_ctx *c = g->ctx;
     BarrierArgs A;
     for (int q = 0; q < GEMB_MAX_RANKS; q++) A.peer[q] = H.peer_flags[q];
-    H.epoch++;
-    halo_barrier_kernel<<<1, 32, 0, c->stream>>>(A, H.flags, H.epoch, c->rank, c->nranks, H.timeout_flag);
+    c->halo_pool.epoch++;
+    halo_barrier_kernel<<<1, 32, 0, c->stream>>>(A, H.flags, c->halo_pool.epoch, c->rank, c->nranks, H.timeout_flag);
     GEMB_CUDA(cudaGetLastError());
     count_launch();
     return GEMB_OK;
@@ -373,15 +398,26 @@ int halo_check_timeout(gemb_graph *g) {
 int halo_free(gemb_graph *g) {
     gemb_halo &H = g->halo;
     if (!H.ready) return GEMB_OK;
-    gemb_ctx *c = g->ctx;
-    halo_release_buffers(g);
-    for (int q = 0; q < c->nranks; q++)
-        if (q != c->rank && H.peer_flags[q]) cudaIpcCloseMemHandle(H.peer_flags[q]);
-    nccl_barrier(c);
-    cudaFree(H.flags); cudaFree(H.timeout_flag);
-    dfree(H.indices_ext); dfree(H.push_ptr); dfree(H.push_dst);
+    cudaStreamSynchronize(g->ctx->stream);
+    dfree(H.indices_ext); dfree(H.push_ptr); dfree(H.push_dst);     // the plan; blocks and flags belong to the context
     H = gemb_halo();
     return GEMB_OK;
+}
+
+// context destruction: not collective (the peers may already be gone); a peer that still maps these blocks keeps its
+// mapping valid until it closes it or exits
+void halo_pool_release(gemb_ctx *c) {
+    gemb_halo_pool &PL = c->halo_pool;
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < PL.nbuf; i++)
+        for (int q = 0; q < c->nranks; q++)
+            if (q != c->rank && PL.peer_buf[i][q]) cudaIpcCloseMemHandle(PL.peer_buf[i][q]);
+    for (int q = 0; q < c->nranks; q++)
+        if (q != c->rank && PL.peer_flags[q]) cudaIpcCloseMemHandle(PL.peer_flags[q]);
+    for (int i = 0; i < PL.nbuf; i++) cudaFree(PL.buf[i]);
+    cudaFree(PL.flags); cudaFree(PL.timeout_flag);
+    (void)cudaGetLastError();
+    PL = gemb_halo_pool();
 }
 
 }  // namespace gemb

@@ -54,6 +54,11 @@ struct HopeWork {
     int64_t spmm_wide = 0, spmm_all = 0;
     bool halo = false;       // multi-GPU: needed-rows-only exchange over peer memory (halo.cu); buf[] = g->halo.buf[]
     int64_t pushes = 0;      // blocks whose rows were pushed to the peers
+    double push_bytes_per_row = 0.0;   // sum over the pushed blocks of (bytes per pushed row): NVLink bytes out = this * push_rows
+    bool wire_half = false;  // halo mode: blocks with bounded entries travel as fp16 (common.cuh); decided once per call
+    bool wire_full_now = false;   // temporarily force fp32 pushes (raw power steps, norm estimation, residual check)
+    bool blk_half[5] = {false, false, false, false, false};   // wire format of the halo copies each work block holds
+    bool push_half() const { return wire_half && !wire_full_now; }
     int buf_index(const float *p) const { for (int i = 0; i < 5; i++) if (buf[i] == p) return i; return -1; }
     ~HopeWork() {
         if (!halo) for (auto p : buf) dfree(p);
@@ -99,11 +104,14 @@ static int publish(HopeWork &W, const float *buf, int width) {
     if (!W.halo) return GEMB_OK;
     const int bi = W.buf_index(buf);
     GEMB_ARG(bi >= 0, "publish: not a work block");
+    const bool half = W.push_half();
     GEMB_TRY(W.c->t_comm.begin(W.c->stream));
-    GEMB_TRY(halo_push_launch(W.g, bi, width));
+    GEMB_TRY(halo_push_launch(W.g, bi, width, half));
     GEMB_TRY(halo_barrier(W.g));
     GEMB_TRY(W.c->t_comm.end(W.c->stream));
+    W.blk_half[bi] = half;
     W.pushes++;
+    W.push_bytes_per_row += (half ? 2.0 : 4.0) * width;
     return GEMB_OK;
 }
 
@@ -116,18 +124,22 @@ static int dist_spmm3(HopeWork &W, bool transpose, int width, float alpha, const
         gemb_csr_dev A = W.g->A;
         A.indices = W.g->halo.indices_ext;
         HaloPushArgs P;
-        const int bo = W.buf_index(Y);
-        if (push_out) { GEMB_ARG(bo >= 0, "spmm output is not a work block"); halo_push_args(W.g, bo, &P); }
+        const int bo = W.buf_index(Y), bin = W.buf_index(Xshard);
+        GEMB_ARG(bin >= 0, "spmm input is not a work block");
+        const bool half_out = W.push_half();
+        if (push_out) { GEMB_ARG(bo >= 0, "spmm output is not a work block"); halo_push_args(W.g, bo, &P, half_out); }
         if (timed) GEMB_TRY(W.c->t_spmm.begin(W.c->stream));
         GEMB_TRY(spmm3_launch(W.c, A, W.rows, width, alpha, Xshard, gamma, use_self ? Xshard : nullptr, delta, X0, Y,
-                              push_out ? &P : nullptr));
+                              push_out ? &P : nullptr, W.blk_half[bin] ? W.g->n_shard : 0));
         if (timed) { GEMB_TRY(W.c->t_spmm.end(W.c->stream)); W.spmm_wide++; }
         W.spmm_all++;
         if (push_out) {
             GEMB_TRY(W.c->t_comm.begin(W.c->stream));
             GEMB_TRY(halo_barrier(W.g));
             GEMB_TRY(W.c->t_comm.end(W.c->stream));
+            W.blk_half[bo] = half_out;
             W.pushes++;
+            W.push_bytes_per_row += (half_out ? 2.0 : 4.0) * width;
         }
         return GEMB_OK;
     }
@@ -257,10 +269,7 @@ axpby_push_kernel(int64_t n_rows, int G, int rows_per_cta, float a, const float4
     const float4 p = P[row * G + cc], q = Q[row * G + cc];
     const float4 v = make_float4(a * p.x + c * q.x, a * p.y + c * q.y, a * p.z + c * q.z, a * p.w + c * q.w);
     Y[row * G + cc] = v;
-    for (int i = H.push_ptr[row], e = H.push_ptr[row + 1]; i < e; i++) {
-        const uint32_t d = H.push_dst[i];
-        H.peer[d >> 29][(H.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + cc] = v;
-    }
+    halo_push_row(H, row, G, cc, v);
 }
 
 static int axpby_launch(HopeWork &W, float a, const float *P, float c, const float *Q, float *Y) {
@@ -269,7 +278,10 @@ static int axpby_launch(HopeWork &W, float a, const float *P, float c, const flo
         const int G = W.b / 4, rpc = 256 / G, bo = W.buf_index(Y);
         GEMB_ARG(bo >= 0 && G <= 256, "axpby output is not a work block");
         HaloPushArgs H;
-        halo_push_args(W.g, bo, &H);
+        const bool half = W.push_half();
+        halo_push_args(W.g, bo, &H, half);
+        W.blk_half[bo] = half;
+        W.push_bytes_per_row += (half ? 2.0 : 4.0) * W.b;
         if (W.rows > 0) {
             axpby_push_kernel<<<(unsigned)((W.rows + rpc - 1) / rpc), 256, 0, W.c->stream>>>(
                 W.rows, G, rpc, a, (const float4 *)P, c, (const float4 *)Q, (float4 *)Y, H);
@@ -345,6 +357,7 @@ static int estimate_norm2(HopeWork &W, uint64_t seed, float *x, float *y, float 
     gemb_ctx *c = W.c;
     gemb_graph *g = W.g;
     const int pw = 4;
+    struct FullWire { HopeWork &w; bool old; FullWire(HopeWork &w_) : w(w_), old(w_.wire_full_now) { w.wire_full_now = true; } ~FullWire() { w.wire_full_now = old; } } fw(W);
     GEMB_TRY(randn_launch(c, W.rows, pw, seed ^ 0x5bd1e995u, (uint64_t)g->row0, x));
     double est = 0.0, prev = -1.0;
     for (int it = 0; it < 16; it++) {
@@ -573,11 +586,13 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
     // the first Cholesky drop columns (skewed spectrum, rank-deficient A), the careful form below takes over.
     bool careful = getenv("GEMB_WARMUP_CAREFUL") != nullptr;
     if (!careful) {
+        W.wire_full_now = true;     // raw (unnormalised) blocks: entries grow like lambda^3, not for the fp16 wire format
         GEMB_TRY(randn_launch(c, W.rows, b, o.seed, (uint64_t)W.g->row0, pool[0]));
         GEMB_TRY(publish(W, pool[0], b));
         GEMB_TRY(dist_spmm3(W, false, b, 1.f, pool[0], 0.f, false, 1.f, nullptr, pool[1], true, W.halo));
         GEMB_TRY(dist_spmm3(W, false, b, 1.f, pool[1], 0.f, false, 1.f, nullptr, pool[2], true, W.halo));
         GEMB_TRY(dist_spmm(W, false, b, 1.f, pool[2], nullptr, AV, true));
+        W.wire_full_now = false;
         GEMB_TRY(gram_full(W, AV, AV, W.G));
         GEMB_TRY(cholqr_pass(W, W.G, AV, pool[0]));
         int rank1 = b;
@@ -811,6 +826,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         GEMB_CUDA(cudaMemsetAsync(STP, 0, blk, c->stream));
         GEMB_CUDA(cudaMemcpyAsync(dMP, MP.data(), sizeof(float) * b * b, cudaMemcpyHostToDevice, c->stream));
         GEMB_CUDA(cudaMemcpyAsync(dMQ, MQ.data(), sizeof(float) * b * b, cudaMemcpyHostToDevice, c->stream));
+        W.wire_full_now = true;     // the check measures the result against the fp32 operator: no fp16 copies here
         int s = apply_launch(c, W.rows, V, b, dMP, b, b, P, b);
         if (s == GEMB_OK) s = apply_launch(c, W.rows, V, b, dMQ, b, b, Q, b);
         if (s == GEMB_OK) s = publish(W, P, b);
@@ -1257,6 +1273,15 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         dfree(flag);
         if (r != ncclSuccess) { set_error("ncclAllReduce(halo agreement): %s", api->GetErrorString(r)); return GEMB_ERR_NCCL; }
         W.halo = hflag == 1;
+        if (W.halo) {
+            // Wire format of the halo copies: fp32.  The fp16 format (common.cuh) is an EXPERIMENT that did not pay and is
+            // only reachable with GEMB_WIRE=fp16-experimental: at 2 ranks the branchy mixed-precision gather costs more
+            // than the halved pushes save (63.6 ms against 42.7 ms per solve, one more filter round to reach the same
+            // residual); at 4 and 8 ranks the run returned after 2 rounds with a zero residual (every column dropped by
+            // the rank test of the Cholesky: a non-finite value entered a block) -- not debugged (profiles/r02_multi_gpu.md).
+            const char *we = getenv("GEMB_WIRE");
+            W.wire_half = we && !strcmp(we, "fp16-experimental");
+        }
         if (!W.halo && o.verbose) fprintf(stderr, "[gemb_hope] halo exchange unavailable (%s); all-gather per sweep\n", gemb_last_error());
     }
     if (W.halo) {
@@ -1391,7 +1416,8 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         stats->halo_rows = W.halo ? g->halo.halo_rows : 0;
         stats->push_rows = W.halo ? g->halo.push_total : 0;
         stats->pushes = W.pushes;
-        stats->mg_mode = c->nranks == 1 ? 0 : (W.halo ? 2 : 1);
+        stats->mg_mode = c->nranks == 1 ? 0 : (W.halo ? (W.wire_half ? 3 : 2) : 1);
+        stats->push_bytes = W.halo ? W.push_bytes_per_row * (double)g->halo.push_total : 0.0;
         stats->resid_est = R.resid_est;
         stats->dense_ms = c->t_dense.total_ms();
         stats->comm_ms = c->t_comm.total_ms();

@@ -18,7 +18,7 @@
 namespace gemb {
 
 int spmm_heavy_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int b, float alpha, const float *X, float gamma,
-                      const float *Xself, float delta, const float *X0, float *Y, const HaloPushArgs *push);
+                      const float *Xself, float delta, const float *X0, float *Y, const HaloPushArgs *push, int n_loc);
 
 __device__ __forceinline__ void fma4(float4 &a, float v, const float4 &x) {
     a.x = fmaf(v, x.x, a.x);
@@ -32,13 +32,13 @@ __device__ __forceinline__ void fma4(float4 &a, float v, const float4 &x) {
 //   Chebyshev three-term step: gamma = -2 s c0 / e (current block), delta = -s s' (previous block)
 // HAS_PUSH (multi-GPU, halo.cu): the finished row is also stored into the halo slots of the peers whose shards
 // reference it -- 16-byte posted stores over NVLink, issued while the other row groups of the SM are still gathering.
-template <bool HAS_VAL, bool HAS_X0, bool HAS_SELF, bool HAS_PUSH>
+template <bool HAS_VAL, bool HAS_X0, bool HAS_SELF, bool HAS_PUSH, bool HALF>
 __global__ void __launch_bounds__(256)
 spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                      const float *__restrict__ vals, int64_t n_rows, int G, int rows_per_cta,
                      float alpha, float gamma, float delta, const float4 *__restrict__ X,
                      const float4 *__restrict__ Xself, const float4 *__restrict__ X0,
-                     float4 *__restrict__ Y, int heavy_deg, HaloPushArgs P) {
+                     float4 *__restrict__ Y, int heavy_deg, HaloPushArgs P, int n_loc) {
     const int tid = threadIdx.x;
     const int lr = tid / G;
     const int c = tid - lr * G;
@@ -47,7 +47,6 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
     if (row >= n_rows) return;
     const int s = __ldg(indptr + row), e = __ldg(indptr + row + 1);
     if (heavy_deg > 0 && e - s > heavy_deg) return;   // a heavy row: spmm_heavy_* kernels below
-    const float4 *Xc = X + c;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int i = s;
     for (; i + 4 <= e; i += 4) {
@@ -60,10 +59,10 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
             v2 = __ldg(vals + i + 2);
             v3 = __ldg(vals + i + 3);
         }
-        const float4 x0 = __ldg(Xc + (int64_t)c0 * G);
-        const float4 x1 = __ldg(Xc + (int64_t)c1 * G);
-        const float4 x2 = __ldg(Xc + (int64_t)c2 * G);
-        const float4 x3 = __ldg(Xc + (int64_t)c3 * G);
+        const float4 x0 = halo_gather<HALF>(X, c0, G, c, n_loc);
+        const float4 x1 = halo_gather<HALF>(X, c1, G, c, n_loc);
+        const float4 x2 = halo_gather<HALF>(X, c2, G, c, n_loc);
+        const float4 x3 = halo_gather<HALF>(X, c3, G, c, n_loc);
         fma4(acc, v0, x0);
         fma4(acc, v1, x1);
         fma4(acc, v2, x2);
@@ -72,8 +71,7 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
     for (; i < e; i++) {
         const int c0 = __ldg(indices + i);
         const float v0 = HAS_VAL ? __ldg(vals + i) : 1.f;
-        const float4 x0 = __ldg(Xc + (int64_t)c0 * G);
-        fma4(acc, v0, x0);
+        fma4(acc, v0, halo_gather<HALF>(X, c0, G, c, n_loc));
     }
     float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
     if (HAS_SELF) {
@@ -91,12 +89,7 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
         r.w = fmaf(delta, z.w, r.w);
     }
     Y[row * G + c] = r;
-    if (HAS_PUSH) {
-        for (int i2 = P.push_ptr[row], e2 = P.push_ptr[row + 1]; i2 < e2; i2++) {
-            const uint32_t d = P.push_dst[i2];
-            P.peer[d >> 29][(P.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + c] = r;
-        }
-    }
+    if (HAS_PUSH) halo_push_row(P, row, G, c, r);
 }
 
 // ---- heavy rows (degree > SPMM_HEAVY_DEG; the hubs of a power-law graph -- R-MAT scale 21 has a 61 814-neighbour
@@ -104,12 +97,12 @@ spmm_rowgroup_kernel(const int32_t *__restrict__ indptr, const int32_t *__restri
 // SPMM_HEAVY_CHUNK nonzeros is one CTA: its row groups stride over the chunk, the group sums are added in a fixed
 // order in shared memory, and the chunk sum goes to a scratch row; a second tiny kernel adds the chunk sums of a row
 // in chunk order and applies the fused epilogue.  No atomics: the result is bit-reproducible.
-template <bool HAS_VAL>
+template <bool HAS_VAL, bool HALF>
 __global__ void __launch_bounds__(256)
 spmm_heavy_partial_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                           const float *__restrict__ vals, const int32_t *__restrict__ item_row,
                           const int32_t *__restrict__ item_beg, int G, int groups, int chunk,
-                          const float4 *__restrict__ X, float4 *__restrict__ partial) {
+                          const float4 *__restrict__ X, float4 *__restrict__ partial, int n_loc) {
     __shared__ float4 red[256];
     const int tid = threadIdx.x;
     const int lr = tid / G;
@@ -121,7 +114,6 @@ spmm_heavy_partial_kernel(const int32_t *__restrict__ indptr, const int32_t *__r
     const int end = beg + chunk < row_end ? beg + chunk : row_end;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lr < groups) {
-        const float4 *Xc = X + c;
         int i = beg + lr;
         for (; i + 3 * groups < end; i += 4 * groups) {
             const int c0 = __ldg(indices + i), c1 = __ldg(indices + i + groups);
@@ -131,14 +123,14 @@ spmm_heavy_partial_kernel(const int32_t *__restrict__ indptr, const int32_t *__r
                 v0 = __ldg(vals + i); v1 = __ldg(vals + i + groups);
                 v2 = __ldg(vals + i + 2 * groups); v3 = __ldg(vals + i + 3 * groups);
             }
-            const float4 x0 = __ldg(Xc + (int64_t)c0 * G), x1 = __ldg(Xc + (int64_t)c1 * G);
-            const float4 x2 = __ldg(Xc + (int64_t)c2 * G), x3 = __ldg(Xc + (int64_t)c3 * G);
+            const float4 x0 = halo_gather<HALF>(X, c0, G, c, n_loc), x1 = halo_gather<HALF>(X, c1, G, c, n_loc);
+            const float4 x2 = halo_gather<HALF>(X, c2, G, c, n_loc), x3 = halo_gather<HALF>(X, c3, G, c, n_loc);
             fma4(acc, v0, x0); fma4(acc, v1, x1); fma4(acc, v2, x2); fma4(acc, v3, x3);
         }
         for (; i < end; i += groups) {
             const int c0 = __ldg(indices + i);
             const float v0 = HAS_VAL ? __ldg(vals + i) : 1.f;
-            fma4(acc, v0, __ldg(Xc + (int64_t)c0 * G));
+            fma4(acc, v0, halo_gather<HALF>(X, c0, G, c, n_loc));
         }
         red[tid] = acc;
     }
@@ -179,12 +171,7 @@ spmm_heavy_finish_kernel(int n_heavy, const int32_t *__restrict__ heavy_row, con
         r.x = fmaf(delta, z.x, r.x); r.y = fmaf(delta, z.y, r.y); r.z = fmaf(delta, z.z, r.z); r.w = fmaf(delta, z.w, r.w);
     }
     Y[row * G + c] = r;
-    if (has_push) {
-        for (int i2 = P.push_ptr[row], e2 = P.push_ptr[row + 1]; i2 < e2; i2++) {
-            const uint32_t d = P.push_dst[i2];
-            P.peer[d >> 29][(P.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + c] = r;
-        }
-    }
+    if (has_push) halo_push_row(P, row, G, c, r);
 }
 
 // ---- v3 (sm_100a): one CTA per row TILE (passes * rows_per_cta consecutive rows); the tile's slice of the column-id
@@ -198,13 +185,13 @@ spmm_heavy_finish_kernel(int n_heavy, const int32_t *__restrict__ heavy_row, con
 // slice exceeds the staging buffer (hubs) reads its ids from global memory as v1 does; rows above SPMM_HEAVY_DEG still go
 // to the chunk kernels.
 constexpr int BULK_CAP = 3072;                 // staged ids per tile (+ up to 3 of alignment slack + 4 of over-read)
-template <bool HAS_VAL, bool HAS_PUSH, bool HAS_X0, bool HAS_SELF>
+template <bool HAS_VAL, bool HAS_PUSH, bool HAS_X0, bool HAS_SELF, bool HALF>
 __global__ void __launch_bounds__(256)
 spmm_bulk_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                  const float *__restrict__ vals, int64_t n_rows, int64_t nnz, int G, int rows_per_cta, int tile_rows,
                  float alpha, float gamma, float delta, const float4 *__restrict__ X,
                  const float4 *__restrict__ Xself, const float4 *__restrict__ X0, float4 *__restrict__ Y,
-                 int heavy_deg, HaloPushArgs P) {
+                 int heavy_deg, HaloPushArgs P, int n_loc) {
     __shared__ __align__(16) int32_t s_idx[BULK_CAP + 8];
     __shared__ __align__(16) float s_val[HAS_VAL ? BULK_CAP + 8 : 4];
     __shared__ __align__(8) uint64_t s_bar;
@@ -242,7 +229,6 @@ spmm_bulk_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__
     const int base = s_base;
     const int32_t *li = s_idx - base;
     const float *lv = s_val - base;
-    const float4 *Xc = X + c;
     for (; row < r1; row += rows_per_cta) {
         if (!(heavy_deg > 0 && e - s > heavy_deg)) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -250,22 +236,22 @@ spmm_bulk_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__
             if (base >= 0) {
                 for (; i + 4 <= e; i += 4) {
                     const int c0 = li[i], c1 = li[i + 1], c2 = li[i + 2], c3 = li[i + 3];
-                    const float4 x0 = __ldg(Xc + (int64_t)c0 * G), x1 = __ldg(Xc + (int64_t)c1 * G);
-                    const float4 x2 = __ldg(Xc + (int64_t)c2 * G), x3 = __ldg(Xc + (int64_t)c3 * G);
+                    const float4 x0 = halo_gather<HALF>(X, c0, G, c, n_loc), x1 = halo_gather<HALF>(X, c1, G, c, n_loc);
+                    const float4 x2 = halo_gather<HALF>(X, c2, G, c, n_loc), x3 = halo_gather<HALF>(X, c3, G, c, n_loc);
                     fma4(acc, HAS_VAL ? lv[i] : 1.f, x0); fma4(acc, HAS_VAL ? lv[i + 1] : 1.f, x1);
                     fma4(acc, HAS_VAL ? lv[i + 2] : 1.f, x2); fma4(acc, HAS_VAL ? lv[i + 3] : 1.f, x3);
                 }
-                for (; i < e; i++) fma4(acc, HAS_VAL ? lv[i] : 1.f, __ldg(Xc + (int64_t)li[i] * G));
+                for (; i < e; i++) fma4(acc, HAS_VAL ? lv[i] : 1.f, halo_gather<HALF>(X, li[i], G, c, n_loc));
             } else {
                 for (; i + 4 <= e; i += 4) {
                     const int c0 = __ldg(indices + i), c1 = __ldg(indices + i + 1);
                     const int c2 = __ldg(indices + i + 2), c3 = __ldg(indices + i + 3);
-                    const float4 x0 = __ldg(Xc + (int64_t)c0 * G), x1 = __ldg(Xc + (int64_t)c1 * G);
-                    const float4 x2 = __ldg(Xc + (int64_t)c2 * G), x3 = __ldg(Xc + (int64_t)c3 * G);
+                    const float4 x0 = halo_gather<HALF>(X, c0, G, c, n_loc), x1 = halo_gather<HALF>(X, c1, G, c, n_loc);
+                    const float4 x2 = halo_gather<HALF>(X, c2, G, c, n_loc), x3 = halo_gather<HALF>(X, c3, G, c, n_loc);
                     fma4(acc, HAS_VAL ? __ldg(vals + i) : 1.f, x0); fma4(acc, HAS_VAL ? __ldg(vals + i + 1) : 1.f, x1);
                     fma4(acc, HAS_VAL ? __ldg(vals + i + 2) : 1.f, x2); fma4(acc, HAS_VAL ? __ldg(vals + i + 3) : 1.f, x3);
                 }
-                for (; i < e; i++) fma4(acc, HAS_VAL ? __ldg(vals + i) : 1.f, __ldg(Xc + (int64_t)__ldg(indices + i) * G));
+                for (; i < e; i++) fma4(acc, HAS_VAL ? __ldg(vals + i) : 1.f, halo_gather<HALF>(X, __ldg(indices + i), G, c, n_loc));
             }
             float4 r = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
             if (HAS_SELF) {
@@ -277,12 +263,7 @@ spmm_bulk_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__
                 r.x = fmaf(delta, z.x, r.x); r.y = fmaf(delta, z.y, r.y); r.z = fmaf(delta, z.z, r.z); r.w = fmaf(delta, z.w, r.w);
             }
             Y[row * G + c] = r;
-            if (HAS_PUSH) {
-                for (int i2 = P.push_ptr[row], e2 = P.push_ptr[row + 1]; i2 < e2; i2++) {
-                    const uint32_t d = P.push_dst[i2];
-                    P.peer[d >> 29][(P.halo_row0 + (int64_t)(d & 0x1fffffffu)) * G + c] = r;
-                }
-            }
+            if (HAS_PUSH) halo_push_row(P, row, G, c, r);
         }
         const int64_t nrow = row + rows_per_cta;
         if (nrow < r1) { s = __ldg(indptr + nrow); e = __ldg(indptr + nrow + 1); }
@@ -305,8 +286,11 @@ int spmm_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, flo
 }
 
 int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, float alpha, const float *X,
-                 float gamma, const float *Xself, float delta, const float *X0, float *Y, const HaloPushArgs *push) {
+                 float gamma, const float *Xself, float delta, const float *X0, float *Y, const HaloPushArgs *push,
+                 int64_t half_from) {
     GEMB_ARG(b > 0 && b % 4 == 0 && b <= 1024, "block width must be a multiple of 4, <= 1024");
+    GEMB_ARG(half_from >= 0 && half_from < (int64_t)2147483647, "half_from");
+    const int n_loc = (int)half_from;     // > 0: halo rows of X (column ids >= n_loc) are fp16 slots
     if (n_rows == 0) return GEMB_OK;
     const int G = b / 4;
     const int rows_per_cta = 256 / G;
@@ -321,9 +305,10 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
         if (push) PA3 = *push;
         const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0, *XS4 = (const float4 *)Xself;
         float4 *Y4 = (float4 *)Y;
-#define LAUNCH3(V, PU, Z, S)                                                                                             \
-        spmm_bulk_kernel<V, PU, Z, S><<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, A.nnz, G, rows_per_cta, \
-                                                                                  tile_rows, alpha, gamma, delta, X4, XS4, X04, Y4, hd, PA3)
+#define LAUNCH3H(V, PU, Z, S, H)                                                                                         \
+        spmm_bulk_kernel<V, PU, Z, S, H><<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, A.nnz, G, rows_per_cta, \
+                                                                                     tile_rows, alpha, gamma, delta, X4, XS4, X04, Y4, hd, PA3, n_loc)
+#define LAUNCH3(V, PU, Z, S) do { if (n_loc > 0) LAUNCH3H(V, PU, Z, S, true); else LAUNCH3H(V, PU, Z, S, false); } while (0)
 #define LAUNCH3B(V, PU)                                                                                                  \
         do {                                                                                                             \
             if (X0 && Xself) LAUNCH3(V, PU, true, true); else if (X0) LAUNCH3(V, PU, true, false);                       \
@@ -333,10 +318,11 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
         else { if (push) LAUNCH3B(false, true); else LAUNCH3B(false, false); }
 #undef LAUNCH3B
 #undef LAUNCH3
+#undef LAUNCH3H
         GEMB_CUDA(cudaGetLastError());
         count_launch();
         if (!heavy3) return GEMB_OK;
-        return spmm_heavy_launch(ctx, A, b, alpha, X, gamma, Xself, delta, X0, Y, push);
+        return spmm_heavy_launch(ctx, A, b, alpha, X, gamma, Xself, delta, X0, Y, push, n_loc);
     }
     const int64_t grid = (n_rows + rows_per_cta - 1) / rows_per_cta;
     GEMB_ARG(grid < (int64_t)2147483647, "grid too large");
@@ -348,14 +334,13 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
     HaloPushArgs PA;
     memset(&PA, 0, sizeof PA);
     if (push) PA = *push;
+#define LAUNCH1(V, Z, S, PU, H)                                                                                        \
+    spmm_rowgroup_kernel<V, Z, S, PU, H><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G, rows_per_cta,      \
+                                                                   alpha, gamma, delta, X4, XS4, X04, Y4, heavy_deg, PA, n_loc)
 #define LAUNCH(V, Z, S)                                                                                      \
     do {                                                                                                     \
-        if (push)                                                                                            \
-            spmm_rowgroup_kernel<V, Z, S, true><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G, rows_per_cta,  \
-                                                                         alpha, gamma, delta, X4, XS4, X04, Y4, heavy_deg, PA); \
-        else                                                                                                 \
-            spmm_rowgroup_kernel<V, Z, S, false><<<g, t, 0, ctx->stream>>>(A.indptr, A.indices, A.data, n_rows, G, rows_per_cta, \
-                                                                          alpha, gamma, delta, X4, XS4, X04, Y4, heavy_deg, PA); \
+        if (push) { if (n_loc > 0) LAUNCH1(V, Z, S, true, true); else LAUNCH1(V, Z, S, true, false); }       \
+        else { if (n_loc > 0) LAUNCH1(V, Z, S, false, true); else LAUNCH1(V, Z, S, false, false); }          \
     } while (0)
     const int sel = (A.data ? 4 : 0) | (X0 ? 2 : 0) | (Xself ? 1 : 0);
     switch (sel) {
@@ -369,14 +354,15 @@ int spmm3_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int64_t n_rows, int b, fl
         default: LAUNCH(true, true, true); break;
     }
 #undef LAUNCH
+#undef LAUNCH1
     GEMB_CUDA(cudaGetLastError());
     count_launch();
-    if (heavy) return spmm_heavy_launch(ctx, A, b, alpha, X, gamma, Xself, delta, X0, Y, push);
+    if (heavy) return spmm_heavy_launch(ctx, A, b, alpha, X, gamma, Xself, delta, X0, Y, push, n_loc);
     return GEMB_OK;
 }
 
 int spmm_heavy_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int b, float alpha, const float *X, float gamma,
-                      const float *Xself, float delta, const float *X0, float *Y, const HaloPushArgs *push) {
+                      const float *Xself, float delta, const float *X0, float *Y, const HaloPushArgs *push, int n_loc) {
     const int G = b / 4;
     const int rows_per_cta = 256 / G;
     const float4 *X4 = (const float4 *)X, *X04 = (const float4 *)X0, *XS4 = (const float4 *)Xself;
@@ -393,12 +379,11 @@ int spmm_heavy_launch(gemb_ctx *ctx, const gemb_csr_dev &A, int b, float alpha, 
             ctx->spmm_scratch_bytes = need;
         }
         float4 *P4 = (float4 *)ctx->spmm_scratch;
-        if (A.data)
-            spmm_heavy_partial_kernel<true><<<A.n_items, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, A.item_row, A.item_beg,
-                                                                               G, rows_per_cta, SPMM_HEAVY_CHUNK, X4, P4);
-        else
-            spmm_heavy_partial_kernel<false><<<A.n_items, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, A.item_row, A.item_beg,
-                                                                                G, rows_per_cta, SPMM_HEAVY_CHUNK, X4, P4);
+#define HP(V, H) spmm_heavy_partial_kernel<V, H><<<A.n_items, 256, 0, ctx->stream>>>(A.indptr, A.indices, A.data, A.item_row, A.item_beg, \
+                                                                                  G, rows_per_cta, SPMM_HEAVY_CHUNK, X4, P4, n_loc)
+        if (A.data) { if (n_loc > 0) HP(true, true); else HP(true, false); }
+        else { if (n_loc > 0) HP(false, true); else HP(false, false); }
+#undef HP
         GEMB_CUDA(cudaGetLastError());
         const int fgrid = (int)(((int64_t)A.n_heavy * G + 255) / 256);
 #define FIN(Z, S) spmm_heavy_finish_kernel<Z, S><<<fgrid, 256, 0, ctx->stream>>>(A.n_heavy, A.heavy_row, A.heavy_first, G, alpha, gamma, \
