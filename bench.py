@@ -478,7 +478,7 @@ def run_hope(args, dist, rank, world, local):
     for _ in range(args.steps):
         _, _, st = g.hope(args.d, beta_arg, want_output=False, **solver)
         dev_ms += st['total_ms']
-        stats = st if stats is None else {k: (stats[k] + st[k] if k in ('spmm_ms', 'dense_ms', 'comm_ms', 'spmm_count', 'pushes') else st[k])
+        stats = st if stats is None else {k: (stats[k] + st[k] if k in ('spmm_ms', 'dense_ms', 'comm_ms', 'spmm_count', 'pushes', 'push_bytes') else st[k])
                                           for k in st}
     dist_barrier(dist, local)
     wall_s = time.perf_counter() - t0
