@@ -29,7 +29,7 @@ class HopeOpts(ctypes.Structure):
                 ('katz_terms', ctypes.c_int32), ('katz_tol', ctypes.c_float), ('seed', ctypes.c_uint64),
                 ('compute_residual', ctypes.c_int32), ('verbose', ctypes.c_int32),
                 ('algorithm', ctypes.c_int32), ('cheb_degree', ctypes.c_int32), ('cheb_range_log2', ctypes.c_float),
-                ('stop_rule', ctypes.c_int32), ('algorithm3_basis', ctypes.c_int32)]
+                ('stop_rule', ctypes.c_int32), ('algorithm3_basis', ctypes.c_int32), ('spectral_mode', ctypes.c_int32)]
 
 
 class HopeStats(ctypes.Structure):
@@ -267,13 +267,13 @@ class DeviceGraph:
                      compute_residual=int(opts.get('compute_residual', 0)), verbose=int(opts.get('verbose', 0)),
                      algorithm=int(opts.get('algorithm', 0)), cheb_degree=int(opts.get('cheb_degree', 0)),
                      cheb_range_log2=float(opts.get('cheb_range_log2', 0.0)), stop_rule=int(opts.get('stop_rule', 0)),
-                     algorithm3_basis=int(opts.get('algorithm3_basis', 0)))
+                     algorithm3_basis=int(opts.get('algorithm3_basis', 0)), spectral_mode=int(opts.get('spectral_mode', 0)))
         st = HopeStats(struct_size=ctypes.sizeof(HopeStats))
         X = sig = None
         if want_output:
             X = out if out is not None else np.empty((self.n_local, d), dtype=np.float32)
             assert X.dtype == np.float32 and X.shape == (self.n_local, d) and X.flags.c_contiguous
-            sig = np.empty(d // 2, dtype=np.float32)
+            sig = np.empty(d if o.spectral_mode else d // 2, dtype=np.float32)
         check(lib().gemb_hope(self._h, int(d), float(beta), ctypes.byref(o), _ptr(X), _ptr(sig), ctypes.byref(st)))
         return X, sig, st.as_dict()
 

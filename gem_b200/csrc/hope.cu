@@ -421,6 +421,8 @@ static int probe_katz_terms(HopeWork &W, float beta, double katz_tol, uint64_t s
 struct Opts {
     int oversample = 16, max_iters = 30, min_iters = 2, katz_terms = 0, compute_residual = 0, verbose = 0;
     int algorithm = 0, cheb_degree = 8, stop_rule = 0, lanczos_basis = 0;
+    int spectral_mode = 0;   // 0: top-k singular triplets of the Katz operator (HOPE); 1: the d largest ALGEBRAIC eigenpairs of the
+                             // uploaded symmetric matrix itself (Laplacian Eigenmaps: D^-1/2 A D^-1/2, lap.py:26-32)
     float tol = 1e-6f, katz_tol = 1e-7f, range_log2 = 8.f;
     uint64_t seed = 1234;
 };
@@ -572,7 +574,8 @@ constexpr int GEMB_SWITCH_TO_LANCZOS = 1000;   // internal status of hope_symmet
 // both sides and the 2 x 16 narrow SpMM sweeps of the power iteration are not needed; hard_bound = ||A||_inf.
 static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double nrm, double hard_bound, HopeResult &R) {
     gemb_ctx *c = W.c;
-    const int b = W.b, k = d / 2;
+    const int mode = o.spectral_mode;
+    const int b = W.b, k = mode ? d : d / 2;
     R.algorithm = 2;
     R.katz_terms = 0;
     float *V = W.buf[0], *AV = W.buf[1];
@@ -671,7 +674,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         }
         for (int i = 0; i < b; i++) {
             const double l = std::max(-bound, std::min(bound, lam[i]));  // Ritz values lie inside the spectrum
-            gval[i] = fabs(katz_f(beta, l));
+            gval[i] = mode ? (l + bound) : fabs(katz_f(beta, l));        // rank key: largest algebraic / largest |f|
         }
         std::iota(order.begin(), order.end(), 0);
         std::sort(order.begin(), order.end(), [&](int a, int c2) { return gval[a] > gval[c2]; });   // descending |f|
@@ -687,7 +690,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         // algorithm = 0 (auto): a first Rayleigh-Ritz round whose wanted values already span more than 3x -- a
         // power-law spectrum -- is a case for restarted Lanczos: a filter that damps everything below the k-th value
         // spreads the wanted columns over g^m and degenerates to power steps
-        if (it == 1 && o.algorithm == 0 && W.g->n >= 2048 && gval[order[k - 1]] < 0.33 * gval[order[0]] &&
+        if (it == 1 && !mode && o.algorithm == 0 && W.g->n >= 2048 && gval[order[k - 1]] < 0.33 * gval[order[0]] &&
             gval[order[std::min(b - 1, 3)]] < 0.7 * gval[order[0]])
             return GEMB_SWITCH_TO_LANCZOS;
         double stop_measure = change;
@@ -710,7 +713,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
                 }
                 const double l = std::max(-bound, std::min(bound, lam[col]));
                 const double r2 = std::max(q - lam[col] * lam[col], 0.0);
-                const double fp = (double)beta / ((1.0 - beta * l) * (1.0 - beta * l));
+                const double fp = mode ? 1.0 : (double)beta / ((1.0 - beta * l) * (1.0 - beta * l));
                 worst = std::max(worst, fp * sqrt(r2) / std::max(gval[order[0]], 1e-300));
             }
             stop_measure = worst;
@@ -724,8 +727,8 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
 
         // damped set {l : |f(l)| < tau}, tau = smallest |f| in the block
         const double tau = gval[order[b - 1]];
-        double hi = tau / ((double)beta * (1.0 + tau));
-        double lo = tau < 1.0 ? -tau / ((double)beta * (1.0 - tau)) : -bound;
+        double hi = mode ? std::max(-bound, std::min(bound, lam[order[b - 1]])) : tau / ((double)beta * (1.0 + tau));
+        double lo = mode ? -bound : (tau < 1.0 ? -tau / ((double)beta * (1.0 - tau)) : -bound);
         lo = std::max(lo, -bound);
         hi = std::min(hi, bound);
         if (hi - lo < 2e-3 * bound) { const double mid = 0.5 * (hi + lo); lo = mid - 1e-3 * bound; hi = mid + 1e-3 * bound; }
@@ -733,7 +736,7 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         np.valid = true;
         np.e = 0.5 * (hi - lo);
         np.c0 = 0.5 * (hi + lo);
-        const double aL = lam[order[0]] >= np.c0 ? bound : -bound;    // normalise p(aL) = 1 at the dominant end
+        const double aL = (mode || lam[order[0]] >= np.c0) ? bound : -bound;    // normalise p(aL) = 1 at the dominant end
         np.sigma1 = np.e / (aL - np.c0);
         // fp32 guard: the filter spreads the block's columns over a dynamic range T_m(x_L) ~ g^m / 2; the
         // Gram-based orthonormalisation squares it, so keep it below ~2^8 (degree m), else take a power step
@@ -765,6 +768,28 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         GEMB_TRY(publish(W, V, b));
     }
 
+    if (mode) {
+        // ---- largest algebraic eigenpairs, DESCENDING (= ascending eigenvalues of I - A_hat, the order lap.py:28-31 sorts into)
+        std::vector<double> Zh((size_t)b * b);
+        GEMB_CUDA(cudaMemcpyAsync(Zh.data(), W.Z, sizeof(double) * b * b, cudaMemcpyDeviceToHost, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<float> M1((size_t)b * k), ev(k);
+        for (int j = 0; j < k; j++) {
+            const int col = order[j];
+            ev[j] = (float)std::max(-bound, std::min(bound, lam[col]));
+            for (int i = 0; i < b; i++) M1[(size_t)i * k + j] = (float)Zh[(size_t)i * b + col];
+        }
+        R.sigma_max = gval[order[0]];
+        GEMB_CUDA(cudaMemcpyAsync(W.M1, M1.data(), sizeof(float) * b * k, cudaMemcpyHostToDevice, c->stream));
+        R.sig_dev = (float *)W.G2;
+        GEMB_CUDA(cudaMemcpyAsync(R.sig_dev, ev.data(), sizeof(float) * k, cudaMemcpyHostToDevice, c->stream));
+        GEMB_CUDA(cudaStreamSynchronize(c->stream));
+        R.Xd = pool[0];
+        GEMB_TRY(c->t_dense.begin(c->stream));
+        GEMB_TRY(apply_launch(c, W.rows, V, b, W.M1, k, k, R.Xd, k));
+        GEMB_TRY(c->t_dense.end(c->stream));
+        return GEMB_OK;
+    }
     // ---- extraction: top k by |f|, ascending sigma
     std::vector<int> sel(order.begin(), order.begin() + k);
     std::reverse(sel.begin(), sel.end());                             // ascending |f|
@@ -1214,7 +1239,8 @@ extern "C" int gemb_hope_svd_error(gemb_graph *g, int d, float beta, const float
 extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts *uo, float *X_out,
                          float *sigma_out, gemb_hope_stats *stats) {
     GEMB_ARG(g != nullptr, "graph");
-    GEMB_ARG(d >= 2 && d % 2 == 0, "d must be even and >= 2");
+    GEMB_ARG(d >= 1, "d must be >= 1");
+    GEMB_ARG((uo && uo->struct_size == sizeof(gemb_hope_opts) && uo->spectral_mode == 1) || d % 2 == 0, "d must be even (k = d/2 singular triplets)");
     GEMB_ARG(!stats || stats->struct_size == sizeof(gemb_hope_stats), "stats.struct_size");
     gemb_ctx *c = g->ctx;
     GEMB_CUDA(cudaSetDevice(c->device));
@@ -1238,13 +1264,21 @@ extern "C" int gemb_hope(gemb_graph *g, int d, float beta, const gemb_hope_opts 
         GEMB_ARG(uo->stop_rule == 0 || uo->stop_rule == 1, "opts.stop_rule");
         o.stop_rule = uo->stop_rule;
         if (uo->algorithm3_basis > 0) o.lanczos_basis = uo->algorithm3_basis;
+        GEMB_ARG(uo->spectral_mode == 0 || uo->spectral_mode == 1, "opts.spectral_mode");
+        o.spectral_mode = uo->spectral_mode;
+    }
+    if (o.spectral_mode == 1) {
+        GEMB_ARG(g->symmetric, "spectral_mode 1 (largest algebraic eigenpairs) needs a symmetric upload");
+        GEMB_ARG(o.algorithm == 0 || o.algorithm == 2, "spectral_mode 1 runs on the Chebyshev-filtered subspace iteration (algorithm 0 or 2)");
+        o.algorithm = 2;
+        beta = 0.f;                 // unused: the ranking is by the eigenvalue itself
     }
     if (o.algorithm >= 2 && !g->symmetric) {
         set_error("algorithm=%d (works on A itself, S = f(A)) needs a symmetric shard (upload with indptr_t = NULL)", o.algorithm);
         return GEMB_ERR_ARG;
     }
     const int algo = o.algorithm ? o.algorithm : (g->symmetric ? 2 : 1);
-    const int k = d / 2;
+    const int k = o.spectral_mode ? d : d / 2;
     GEMB_ARG((int64_t)k <= g->n, "d/2 must not exceed the number of nodes");
     int64_t bb = std::min<int64_t>(g->n, (int64_t)k + o.oversample);
     int b = (int)((bb + 3) / 4 * 4);

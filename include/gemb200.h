@@ -141,6 +141,11 @@ typedef struct {
                                   from the Rayleigh-Ritz products (algorithm 2: |f'(l_j)| ||A v_j - l_j v_j||) */
     int32_t algorithm3_basis; /* algorithm 3 (thick-restart block Lanczos on A, symmetric A): maximum basis width,
                               0 = default (max(2k + 64, 192) rounded to the block) */
+    int32_t spectral_mode; /* 0 = HOPE (top d/2 singular triplets of the Katz operator).
+                              1 = the d largest ALGEBRAIC eigenpairs of the uploaded symmetric matrix itself, on the same
+                              Chebyshev-filtered subspace iteration (beta ignored): X_out = n x d eigenvectors in DESCENDING
+                              eigenvalue order, sigma_out = the d eigenvalues.  Laplacian Eigenmaps (lap.py:26-32:
+                              eigs(normalized_laplacian, k = d+1, which='SM')) = this on D^-1/2 A D^-1/2 with d+1 pairs */
 } gemb_hope_opts;
 
 typedef struct {

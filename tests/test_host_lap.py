@@ -1,0 +1,45 @@
+"""Host logic of gem_b200.embedding.lap (CPU): the undirected, degree-normalised matrix the GPU solver receives equals
+I - L_sym of the pinned oracle (oracle/lap_oracle.py <- nx.normalized_laplacian_matrix(graph.to_undirected()), lap.py:25-26),
+including networkx's rule for a pair whose two directions carry different weights, self loops and isolated vertices."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import REPO
+
+sys.path.insert(0, os.path.join(REPO, 'oracle'))
+
+
+def test_undirected_normalised_matches_oracle():
+    import networkx as nx
+    import lap_oracle as lo
+    from gem_b200 import graph as hg
+    from gem_b200.embedding.lap import undirected_normalised
+    rng = np.random.default_rng(5)
+    G = nx.DiGraph()
+    G.add_nodes_from(range(60))                       # nodes 57..59 stay isolated
+    for _ in range(400):
+        u, v = int(rng.integers(0, 57)), int(rng.integers(0, 57))
+        G.add_edge(u, v, weight=float(np.round(rng.uniform(0.3, 2.5), 3)))      # includes a few self loops
+    csr = hg.from_networkx(G)
+    ahat, l_fro2 = undirected_normalised(csr)
+    A = nx.to_scipy_sparse_array(G, nodelist=list(G.nodes), weight='weight', format='csr')
+    W = lo.undirected_weights(A)
+    assert np.array_equal(W.toarray(), nx.to_numpy_array(G.to_undirected(), nodelist=list(G.nodes), weight='weight'))
+    L = lo.normalized_laplacian(W).toarray()
+    assert np.allclose(ahat.to_scipy().toarray(), np.eye(60) - L, atol=1e-14)
+    assert abs(l_fro2 - np.sum(L * L)) < 1e-10
+    assert ahat.is_symmetric()
+
+
+def test_errors_and_names():
+    from gem_b200.embedding.lap import LaplacianEigenmaps
+    LaplacianEigenmaps.hyper_params.clear(); LaplacianEigenmaps.hyper_params.update({'method_name': 'lap_eigmap_svd'})
+    m = LaplacianEigenmaps(d=2)
+    assert m.get_method_name() == 'lap_eigmap_svd' and m.get_method_summary() == 'lap_eigmap_svd_2'
+    with pytest.raises(ValueError, match='graph needed'):
+        m.learn_embedding(graph=None)
+    with pytest.raises(ValueError, match='Embedding not learned yet'):
+        m.get_embedding()
