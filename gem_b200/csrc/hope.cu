@@ -472,7 +472,9 @@ static int hope_general(HopeWork &W, const Opts &o, int d, float beta, int J, Ho
         GEMB_TRY(gram_full(W, U, U, W.G));                            // T = U^T U
         GEMB_CUDA(cudaMemcpyAsync(W.G2, W.G, sizeof(double) * b * b, cudaMemcpyDeviceToDevice, c->stream));
         GEMB_TRY(c->t_dense.begin(c->stream));
-        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs, std::min(1e-7, std::max(1e-13, 1e-3 * (double)o.tol))));
+        // Jacobi accuracy follows the requested tolerance (Z only pre-rotates the CholeskyQR and forms the Ritz vectors:
+        // an off-diagonal remainder of 1e-2 tol is invisible at tol; one sweep less per round at the bench setting)
+        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs, std::min(1e-5, std::max(1e-13, 1e-2 * (double)o.tol))));
         GEMB_TRY(c->t_dense.end(c->stream));
         GEMB_CUDA(cudaMemcpyAsync(theta.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
         GEMB_CUDA(cudaStreamSynchronize(c->stream));
@@ -662,7 +664,9 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         // round's interval costs two extra rounds -- 75 instead of 56 SpMM sweeps -- and is slower overall;
         // the eigen-decomposition therefore stays on the critical path.)
         GEMB_TRY(c->t_dense.begin(c->stream));
-        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs, std::min(1e-7, std::max(1e-13, 1e-3 * (double)o.tol))));
+        // Jacobi accuracy follows the requested tolerance (Z only pre-rotates the CholeskyQR and forms the Ritz vectors:
+        // an off-diagonal remainder of 1e-2 tol is invisible at tol; one sweep less per round at the bench setting)
+        GEMB_TRY(eigh_launch(c, b, W.G2, W.w, W.Z, W.Zs, std::min(1e-5, std::max(1e-13, 1e-2 * (double)o.tol))));
         GEMB_TRY(c->t_dense.end(c->stream));
         GEMB_CUDA(cudaMemcpyAsync(lam.data(), W.w, sizeof(double) * b, cudaMemcpyDeviceToHost, c->stream));
         GEMB_CUDA(cudaStreamSynchronize(c->stream));
