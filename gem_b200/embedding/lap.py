@@ -24,13 +24,11 @@ from gem_b200.embedding.static_graph_embedding import StaticGraphEmbedding
 _OPT_KEYS = ('tol', 'max_iters', 'min_iters', 'oversample', 'seed', 'verbose', 'cheb_degree', 'cheb_range_log2', 'stop_rule')
 
 
-def undirected_normalised(csr):
-    """(HostCSR of A_hat' = D^-1/2 W D^-1/2 + [isolated vertices: 1 on the diagonal], ||L_sym||_F^2).
-    W = graph.to_undirected() of lap.py:25 on the adjacency matrix: the pair {u, v} exists when either direction does; when
+def undirected_coo(csr):
+    """graph.to_undirected() (lap.py:25, lle.py:25) on the adjacency matrix, as symmetric COO (src, dst, weight) with every
+    off-diagonal pair in both directions and the self loops once.  The pair {u, v} exists when either direction does; when
     both do, networkx copies the nodes in order and, for each, its out-edges, so the edge out of the LATER node is written
-    last and wins: W[u, v] = A[max, min] if present, else A[min, max].  D = row sums of W, 1/sqrt(0) -> 0
-    (nx.normalized_laplacian_matrix).  An isolated vertex has a zero row in L_sym (eigenvalue 0, eigenvector e_i); a unit
-    self loop in A_hat' gives it the matching eigenvalue 1."""
+    last and wins: W[u, v] = A[max, min] if present, else A[min, max]."""
     n = csr.n
     rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(csr.indptr).astype(np.int64))
     cols = csr.indices.astype(np.int64)
@@ -46,9 +44,15 @@ def undirected_normalised(csr):
     sel = order[first]
     pl, ph, pw = lo[sel], hi[sel], w[off][sel]
     dr, dw = rows[~off], w[~off]                             # self loops stay as they are
-    src = np.concatenate((pl, ph, dr))
-    dst = np.concatenate((ph, pl, dr))
-    ww = np.concatenate((pw, pw, dw))
+    return np.concatenate((pl, ph, dr)), np.concatenate((ph, pl, dr)), np.concatenate((pw, pw, dw))
+
+
+def undirected_normalised(csr):
+    """(HostCSR of A_hat' = D^-1/2 W D^-1/2 + [isolated vertices: 1 on the diagonal], ||L_sym||_F^2), W = undirected_coo.
+    D = row sums of W, 1/sqrt(0) -> 0 (nx.normalized_laplacian_matrix).  An isolated vertex has a zero row in L_sym
+    (eigenvalue 0, eigenvector e_i); a unit self loop in A_hat' gives it the matching eigenvalue 1."""
+    n = csr.n
+    src, dst, ww = undirected_coo(csr)
     deg = np.bincount(src, weights=ww, minlength=n)
     with np.errstate(divide='ignore'):
         dh = 1.0 / np.sqrt(deg)
@@ -56,9 +60,9 @@ def undirected_normalised(csr):
     ah = ww * dh[src] * dh[dst]
     iso = np.flatnonzero(deg == 0)
     # ||L_sym||_F^2 = sum_i (1[deg_i > 0] - A_hat_ii)^2 + sum_{i != j} A_hat_ij^2
-    diag_hat = np.bincount(dr, weights=dw * dh[dr] * dh[dr], minlength=n) if dr.size else np.zeros(n)
-    offm = src != dst
-    l_fro2 = float(np.sum(((deg > 0).astype(np.float64) - diag_hat) ** 2) + np.sum(ah[offm] ** 2))
+    dm = src == dst
+    diag_hat = np.bincount(src[dm], weights=ah[dm], minlength=n) if dm.any() else np.zeros(n)
+    l_fro2 = float(np.sum(((deg > 0).astype(np.float64) - diag_hat) ** 2) + np.sum(ah[~dm] ** 2))
     src = np.concatenate((src, iso)); dst = np.concatenate((dst, iso)); ah = np.concatenate((ah, np.ones(iso.shape[0])))
     out = _graph.from_edges(n, src, dst, ah, nodes=csr.nodes, unit_if_all_ones=False)
     out.symmetric = True

@@ -43,3 +43,29 @@ def test_errors_and_names():
         m.learn_embedding(graph=None)
     with pytest.raises(ValueError, match='Embedding not learned yet'):
         m.get_embedding()
+
+
+def test_lle_operator_matches_oracle():
+    """gem_b200.embedding.lle.lle_operator: C = c I - (I - P)^T (I - P) against the pinned oracle's I - P (lle.py:25-28)."""
+    import networkx as nx
+    import lle_oracle as le
+    from gem_b200 import graph as hg
+    from gem_b200.embedding.lle import lle_operator, LocallyLinearEmbedding
+    rng = np.random.default_rng(8)
+    G = nx.DiGraph()
+    G.add_nodes_from(range(50))                       # 48, 49 isolated
+    for _ in range(300):
+        u, v = int(rng.integers(0, 48)), int(rng.integers(0, 48))
+        if u != v:
+            G.add_edge(u, v, weight=float(np.round(rng.uniform(0.3, 2.5), 3)))
+    C, c = lle_operator(hg.from_networkx(G))
+    A = nx.to_scipy_sparse_array(G, nodelist=list(G.nodes), weight='weight', format='csr')
+    M = le.lle_matrix(A).toarray()
+    assert c >= np.linalg.norm(M, 2) ** 2 - 1e-12
+    assert np.allclose(C.to_scipy().toarray(), c * np.eye(50) - M.T @ M, atol=1e-13)
+    assert C.is_symmetric()
+    LocallyLinearEmbedding.hyper_params.clear(); LocallyLinearEmbedding.hyper_params.update({'method_name': 'lle_svd'})
+    m = LocallyLinearEmbedding(d=2)
+    assert m.get_method_summary() == 'lle_svd_2'
+    with pytest.raises(ValueError, match='graph needed'):
+        m.learn_embedding(graph=None)
