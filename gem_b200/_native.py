@@ -19,7 +19,7 @@ EXPORTS = [
     'gemb_host_alloc', 'gemb_host_free', 'gemb_mem_trim', 'gemb_mem_cached_bytes', 'gemb_comm_unique_id', 'gemb_comm_init', 'gemb_graph_upload',
     'gemb_graph_free', 'gemb_spmm', 'gemb_gram', 'gemb_apply', 'gemb_hope', 'gemb_hope_svd_error', 'gemb_n2v_alias', 'gemb_n2v_walks', 'gemb_node2vec',
     'gemb_edge_list_scan', 'gemb_edge_list_parse', 'gemb_edge_list_write', 'gemb_emb_read', 'gemb_emb_write',
-    'gemb_synth_rmat', 'gemb_recon_create', 'gemb_recon_free', 'gemb_recon_dense', 'gemb_recon_pairs', 'gemb_recon_ranks', 'gemb_recon_top',
+    'gemb_synth_rmat', 'gemb_gf', 'gemb_recon_create', 'gemb_recon_free', 'gemb_recon_dense', 'gemb_recon_pairs', 'gemb_recon_ranks', 'gemb_recon_top',
 ]
 
 
@@ -103,6 +103,7 @@ def lib():
     L.gemb_emb_write.argtypes = [cp, i64, vp, i32, vp, i64]
     L.gemb_synth_rmat.argtypes = [vp, ctypes.c_int, ctypes.c_int, f64, f64, f64, ctypes.c_uint64, ctypes.c_int, i64, i64,
                                   ctypes.POINTER(i64), ctypes.POINTER(i64), vp, vp, i64]
+    L.gemb_gf.argtypes = [vp, i64, i64, vp, vp, vp, ctypes.c_int, f32, f32, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(f64)]
     L.gemb_recon_create.argtypes = [vp, vp, i64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
     L.gemb_recon_free.argtypes = [vp]
     L.gemb_recon_dense.argtypes = [vp, vp]
@@ -215,6 +216,20 @@ def synth_rmat(ctx, scale, edge_factor=8, a=0.57, b=0.19, c=0.19, seed=42, permu
     indices = np.empty(max(int(nnz.value), 1), dtype=np.int32)
     check(lib().gemb_synth_rmat(*args, ctypes.byref(nnz), ctypes.byref(tot), _ptr(indptr), _ptr(indices), int(indices.shape[0])))
     return indptr, indices[:int(nnz.value)], int(tot.value)
+
+
+def graph_factorization(ctx, n, src, dst, w, d, eta, regu, max_iter, X0, mode=0):
+    """gemb_gf: the edge SGD of gf.py:94-104 on the device.  Returns (X n x d float32, device ms)."""
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    dst = np.ascontiguousarray(dst, dtype=np.int32)
+    w = None if w is None else np.ascontiguousarray(w, dtype=np.float32)
+    X0 = np.ascontiguousarray(X0, dtype=np.float32)
+    assert X0.shape == (int(n), int(d)) and src.shape == dst.shape
+    X = np.empty_like(X0)
+    ms = ctypes.c_double(0.0)
+    check(lib().gemb_gf(ctx._h, int(n), int(src.shape[0]), _ptr(src), _ptr(dst), _ptr(w), int(d), float(eta), float(regu),
+                        int(max_iter), int(mode), _ptr(X0), _ptr(X), ctypes.byref(ms)))
+    return X, float(ms.value)
 
 
 def comm_unique_id():

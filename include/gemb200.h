@@ -61,6 +61,16 @@ int gemb_host_free(void *p);
 int gemb_mem_trim(void);
 size_t gemb_mem_cached_bytes(void);
 
+/* ---- Graph Factorization.  Replaces the edge SGD of gem/embedding/gf.py:94-104 (its C++ twin:
+ * gem/c_src/gf.cpp:143-164; the reference shells out to gem/c_exe/gf when it exists and then runs the Python loop anyway):
+ *     for epoch in range(max_iter): for (i, j, w) in edges, j > i:  X[i] -= eta * (regu * X[i] - (w - <X[i], X[j]>) * X[j])
+ * src / dst / w: the m directed edges (host; w NULL = 1).  X0: the n x d start (the reference draws 0.01 * randn), X_out: n x d.
+ * mode 0: one warp applies the edges in the order given, epoch after epoch (the reference's sequential sweep, fp32).
+ * mode 1: one warp per source row (edges grouped by src, in order), partner rows read from the previous epoch's table
+ *         (Jacobi across rows, Gauss-Seidel inside a row): deterministic, for graphs beyond the reference's reach. */
+int gemb_gf(gemb_ctx *ctx, int64_t n, int64_t m, const int32_t *src, const int32_t *dst, const float *w, int d, float eta,
+            float regu, int max_iter, int mode, const float *X0, float *X_out, double *device_ms_out);
+
 /* ---- bench infrastructure: Graph500 R-MAT generator on the device (BASELINE.json configs[3], configs[4]: scale 24).
  * No reference counterpart (GEM ships no generator; gem/tests load fixed fixtures); the host generator
  * gem_b200/synth.py::rmat makes the same kind of graph with NumPy for the small parity cases.

@@ -69,3 +69,21 @@ def test_lle_operator_matches_oracle():
     assert m.get_method_summary() == 'lle_svd_2'
     with pytest.raises(ValueError, match='graph needed'):
         m.learn_embedding(graph=None)
+
+
+def test_gf_host_logic():
+    import networkx as nx
+    from gem_b200.embedding.gf import GraphFactorization
+    GraphFactorization.hyper_params.clear()
+    GraphFactorization.hyper_params.update({'print_step': 10000, 'method_name': 'graph_factor_sgd'})
+    m = GraphFactorization(d=2, max_iter=10, eta=1e-3, regu=1.0, data_set='x')
+    assert m.get_method_summary() == 'graph_factor_sgd_2'
+    with pytest.raises(ValueError, match='graph needed'):
+        m.learn_embedding(graph=None)
+    G = nx.DiGraph()
+    G.add_edge(2, 0, weight=0.5); G.add_edge(0, 1); G.add_node(3)
+    n, src, dst, w = m._edges(G)
+    assert n == 4 and src.tolist() == [2, 0] and dst.tolist() == [0, 1] and w.tolist() == [0.5, 1.0]      # graph.edges order
+    H = nx.DiGraph(); H.add_edge(5, 1)
+    with pytest.raises(ValueError, match='labels must be 0..n-1'):
+        m._edges(H)
