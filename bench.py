@@ -321,7 +321,7 @@ def run_reference(args):
         n_s = args.cpu_sample or args.n
         A = synth.sbm(n=n_s, block=min(1000, n_s), seed=42).to_scipy()
         secs, info = [], None
-        budget_s = float(os.environ.get('GEMB_REF_BUDGET_S', '600'))
+        budget_s = float(os.environ.get('GEMB_REF_BUDGET_S', '420'))      # a second solve starts only if it would end inside this
         # projected time of ONE solve from the calibrated operator: ~1500 operator applications of J = 11 sweeps (ARPACK
         # eigsh on S^T S, k = 64, tol 1e-3, on this spectrum), scaled by what the box measured; if that does not fit the
         # budget the graph is shrunk proportionally (stated in the line) instead of running past the driver's patience
