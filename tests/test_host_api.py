@@ -200,3 +200,25 @@ def test_device_graph_refuses_offsets_beyond_int32():
     ip = np.array([0, 2 ** 31], dtype=np.int64)
     with pytest.raises(ValueError, match='int32 offsets'):
         _native.DeviceGraph(FakeCtx(), 1, ip, np.zeros(1, np.int32))
+
+
+def test_bench_reference_arm_contract(tmp_path):
+    """`bench.py --impl reference` (the CPU arm the driver runs first): one JSON line with the contract's keys, on a tiny sample."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    env = dict(os.environ, OMP_NUM_THREADS='2')
+    p = subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--cpu-sample', '3000', '--steps', '1',
+                        '--warmup', '0'], capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads([l for l in p.stdout.splitlines() if l.startswith('{')][-1])
+    assert line['impl'] == 'reference' and line['metric'].startswith('nodes/sec embedded') and line['unit'] == 'nodes/s'
+    assert line['value'] > 0 and line['higher_is_better'] is True and line['n_gpus'] == 1
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['value'] == line['value'] and line['e2e']['h2d_bytes_per_step'] == 0
+    # under torchrun every rank but 0 prints nothing and exits 0
+    p1 = subprocess.run([sys.executable, os.path.join(REPO, 'bench.py'), '--impl', 'reference', '--cpu-sample', '3000'],
+                        capture_output=True, text=True, timeout=60, env=dict(env, RANK='1', WORLD_SIZE='2'), cwd=str(tmp_path))
+    assert p1.returncode == 0 and p1.stdout.strip() == ''
