@@ -87,3 +87,34 @@ def test_gf_host_logic():
     H = nx.DiGraph(); H.add_edge(5, 1)
     with pytest.raises(ValueError, match='labels must be 0..n-1'):
         m._edges(H)
+
+
+def test_gf_schedule_choice(monkeypatch):
+    """Which gemb_gf mode the plugin asks for: rows in parallel when graph.edges() is grouped by ascending source, the reference's
+    order on one warp otherwise, regrouping (with a warning) beyond sequential_limit."""
+    import networkx as nx
+    from gem_b200 import _native
+    from gem_b200.embedding.gf import GraphFactorization
+    calls = []
+
+    class FakeCtx:
+        def __init__(self, device=0): pass
+        def close(self): pass
+
+    def fake_gf(ctx, n, src, dst, w, d, eta, regu, max_iter, X0, mode=0):
+        calls.append((mode, src.tolist()))
+        return np.zeros((n, d), np.float32), 0.0
+
+    monkeypatch.setattr(_native, 'Context', FakeCtx)
+    monkeypatch.setattr(_native, 'graph_factorization', fake_gf)
+    GraphFactorization.hyper_params.clear()
+    GraphFactorization.hyper_params.update({'print_step': 10000, 'method_name': 'graph_factor_sgd'})
+    G = nx.DiGraph(); G.add_nodes_from(range(4)); G.add_edges_from([(0, 1), (1, 2), (2, 3), (3, 0)])
+    GraphFactorization(d=2, max_iter=5, eta=1e-3, regu=1.0).learn_embedding(graph=G)
+    assert calls[-1][0] == 1
+    H = nx.DiGraph(); H.add_edges_from([(2, 3), (0, 1), (1, 2)])            # node order 2, 3, 0, 1: sources 2, 0, 1
+    GraphFactorization(d=2, max_iter=5, eta=1e-3, regu=1.0).learn_embedding(graph=H)
+    assert calls[-1] == (0, [2, 0, 1])
+    with pytest.warns(RuntimeWarning, match='grouped by source'):
+        GraphFactorization(d=2, max_iter=5, eta=1e-3, regu=1.0, sequential_limit=10).learn_embedding(graph=H)
+    assert calls[-1] == (1, [0, 1, 2])
