@@ -85,7 +85,6 @@ struct gemb_ctx {
     // multi-GPU
     int rank = 0, nranks = 1;
     void *comm = nullptr;  // ncclComm_t
-    int *tile_counter = nullptr;  // device work counter of the persistent SpMM kernel
     float *spmm_scratch = nullptr;   // chunk partial sums of the heavy rows (n_items x b), grown on demand
     size_t spmm_scratch_bytes = 0;
     gemb::Timer t_spmm, t_dense, t_comm, t_misc;

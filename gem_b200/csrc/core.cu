@@ -227,7 +227,6 @@ int gemb_ctx_destroy(gemb_ctx *c) {
     c->t_dense.destroy();
     c->t_comm.destroy();
     c->t_misc.destroy();
-    dfree(c->tile_counter);
     dfree(c->spmm_scratch);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -747,10 +747,10 @@ static int hope_symmetric(HopeWork &W, const Opts &o, int d, float beta, double 
         const double xL = fabs(aL - np.c0) / np.e;
         const double growth = xL + sqrt(std::max(xL * xL - 1.0, 0.0));
         np.deg = o.cheb_degree;
-        // GEMB_CHEB_RANGE_LOG2 (default 8) is the experiment knob for this guard: an fp32 NumPy model of this loop
-        // (scripts/proto_bcgs.py) says that the column scaling inside the Ritz-rotated CholeskyQR tolerates far
-        // more than 2^8 on the SBM spectrum (degree 12: residual 3.8e-3 after 4 rounds / 40 sweeps instead of 4.9e-3
-        // after 8 rounds / 56 sweeps), which is to be confirmed on the GPU before the default moves.
+        // opts.cheb_range_log2 (default 8; GEMB_CHEB_RANGE_LOG2 overrides it for experiments): the column scaling inside the
+        // Ritz-rotated CholeskyQR tolerates far more than 2^8 on the SBM spectrum -- measured in profiles/r02c_solver_sweep.md:
+        // 2^14 with degree 16 reaches a residual of 3.0e-3 in 4 rounds / 42 sweeps (the bench setting) where 2^8 with degree 8
+        // needed 8 rounds / 56 sweeps for 4.0e-3.  The library default stays conservative (tight-tolerance solves).
         const double range_log2 = getenv("GEMB_CHEB_RANGE_LOG2") ? atof(getenv("GEMB_CHEB_RANGE_LOG2")) : (double)o.range_log2;
         if (growth > 1.0 + 1e-9) np.deg = std::min(np.deg, (int)floor(log(2.0 * exp2(range_log2)) / log(growth)));
 
