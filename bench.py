@@ -516,7 +516,8 @@ def run_hope(args, dist, rank, world, local):
     achieved = stats['spmm_bytes'] / (spmm_ms_per * 1e-3) / 1e9 if spmm_ms_per > 0 else 0.0
     traffic = None
     tp = os.path.join(REPO, 'profiles', 'spmm_traffic.json')
-    if os.path.exists(tp):
+    # the ncu capture is of THIS workload on one GPU (SBM 1M, block 72): no traffic figure for other graphs / shardings
+    if os.path.exists(tp) and not rmat and world == 1 and stats['block'] == 72 and args.n == 1_000_000:
         try:
             traffic = json.load(open(tp)).get('dram_bytes_per_launch')
         except Exception:
