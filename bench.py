@@ -676,7 +676,8 @@ def run_node2vec(args, dist, rank, world, local):
     sg_bytes = pairs * 14 * 4 * args.d
     achieved = sg_bytes / world / (agg['sgns_ms'] * 1e-3) / 1e9 if agg['sgns_ms'] > 0 else 0.0
     roofline = {'kernel': 'sgns (warp per walk, fp32 tables)', 'bound': 'hbm', 'achieved': achieved,
-                'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': n2v_traffic(),
+                'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'],
+                'traffic': n2v_traffic() if (not rmat and world == 1 and args.n == 1_000_000 and (args.d, args.walk_len, args.num_walks, args.con_size) == (128, 80, 10, 10)) else None,
                 'peak_source': peak_src, 'bytes_per_launch': sg_bytes / world / args.steps,
                 'ms_per_launch': agg['sgns_ms'] / args.steps, 'share_of_step': agg['sgns_ms'] / max(dev_ms, 1e-9),
                 'note': 'algorithmic bytes = 7168 B per (centre, context) pair (SURVEY 8(d)); rows of the walk and the '
